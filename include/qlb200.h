@@ -1,0 +1,137 @@
+/*
+ * qlb200.h -- C ABI of libqlb200.so, the B200-native Fock-build engine behind QuantumLab.jl's SCF hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes and returns an int status (0 = ok,
+ * non-zero = error; qlb_last_error() gives the message).  There is NO CPU fallback: every compute entry
+ * point fails with QLB_ERR_CUDA if no sm_100-class device is usable.
+ *
+ * The reference interface each entry point replaces is QuantumLab.jl's only FFI seam, the libint2 shim
+ * (deps/usr/src/libint2jl.cpp, bound by src/SubModules/LibInt2Module.jl), plus the Julia functions that
+ * sit directly above it on the hot path.  Citations are file:line relative to the reference checkout.
+ *
+ * Conventions (identical to the reference's native Julia path):
+ *   - all matrices / tensors are column-major double, first index fastest, in the reference's basis
+ *     function order: shells in the order given, Cartesian components x-descending then y-descending
+ *     (BaseModule.jl:110-122), e.g. d = xx,xy,xz,yy,yz,zz;
+ *   - shell coefficients arrive already normalised the way the Shell constructor leaves them
+ *     (ShellModule.jl:25-48); the non-axial factors of ShellModule.jl:50-58 (d_xy: sqrt 3) are applied
+ *     on the device, so outputs equal the native Julia values directly;
+ *   - the density P is the reference's P = Cocc*Cocc' (no factor 2, HartreeFockModule.jl:82), symmetric.
+ */
+#ifndef QLB200_H
+#define QLB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QLB_OK 0
+#define QLB_ERR_ARG 1       /* bad argument (null pointer, L > QLB_MAX_L, ...)            */
+#define QLB_ERR_CUDA 2      /* CUDA runtime / launch failure, or no usable device           */
+#define QLB_ERR_STATE 3     /* qlb_init not called, handle destroyed, ...                   */
+#define QLB_ERR_NCCL 4      /* collective failure                                           */
+#define QLB_ERR_NOMEM 5
+
+#define QLB_MAX_L 2         /* highest shell angular momentum with ERI class kernels (s,p,d) */
+#define QLB_NCLASS 6        /* shell-pair classes ss,ps,pp,ds,dp,dd                          */
+#define QLB_NQCLASS 21      /* canonical (bra class >= ket class) quartet classes            */
+
+typedef struct qlb_basis qlb_basis; /* opaque: device-resident shells, shell pairs, Schwarz bounds */
+
+/* Per-build statistics (all counts are exact integers; times are CUDA-event milliseconds). */
+typedef struct qlb_stats {
+  int64_t quartets_unique;            /* unique shell quartets npair*(npair+1)/2 (before screening)        */
+  int64_t quartets_kept;              /* quartets that passed the integer Schwarz x density rule            */
+  int64_t quartets_kept_class[QLB_NQCLASS];      /* the same, per canonical L-class                         */
+  int64_t prim_quartets_class[QLB_NQCLASS];      /* primitive quartets evaluated, per class                 */
+  int64_t pairs_total;                /* unique shell pairs                                                  */
+  int64_t pairs_significant;          /* pairs that can survive with the current tau and density            */
+  double ms_total;                    /* whole call, on the device timeline (events on the build stream)     */
+  double ms_eri;                      /* the ERI/digestion class kernels only                                */
+  double ms_class[QLB_NQCLASS];       /* per class kernel (only filled when profiling is switched on)        */
+  double flops_algorithmic;           /* SURVEY.md 8(d) minimum-MD flop count for what was evaluated          */
+  int32_t kernel_launches;            /* kernels launched by this call                                       */
+  int32_t reserved;
+} qlb_stats;
+
+/* ---- lifetime -----------------------------------------------------------------------------------------
+ * replaces libint2start()/libint2stop()  (libint2jl.cpp:3-9, LibInt2Module.jl:30-40).
+ * device < 0 selects the current device.  One engine per process (one process per GPU). */
+int qlb_init(int device);
+int qlb_finalize(void);
+const char *qlb_last_error(void);
+int qlb_device_info(char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- basis ---------------------------------------------------------------------------------------------
+ * replaces createShell() per shell (libint2jl.cpp:11-24, LibInt2Module.jl:70-104) and
+ * createEngineCoulomb()/destroyEngine() (libint2jl.cpp:53-60,88-93): the handle owns the device copy of the
+ * shells AND the geometry-only precomputation the reference redoes per primitive quartet
+ * (GaussProductFundamental, IntegralsModule.jl:66-83): primitive-pair records, Schwarz bounds, class bins.
+ *   centers: 3*nsh (bohr)   L: nsh   nprim: nsh   exps/coefs: concatenated per shell. */
+int qlb_basis_create(int nsh, const double *centers, const int32_t *L, const int32_t *nprim,
+                     const double *exps, const double *coefs, qlb_basis **out);
+int qlb_basis_destroy(qlb_basis *b);
+int qlb_basis_nbf(const qlb_basis *b, int *nbf);
+int qlb_basis_npairs(const qlb_basis *b, int64_t *npairs);
+
+/* ---- ERI entry points of IntegralsModule -----------------------------------------------------------------
+ * qlb_eri_block  replaces compute4cInts() (libint2jl.cpp:100-103) as used by
+ *   computeTensorBlockElectronRepulsionIntegrals (LibInt2Module.jl:319-334, SpecialMatricesModule.jl:184-186):
+ *   out[mu + nA*(nu + nB*(la + nC*si))] = (mu nu|la si) for shells (i,j,k,l) (0-based), non-axial factors applied.
+ * qlb_eri_tensor replaces computeTensorElectronRepulsionIntegrals (SpecialMatricesModule.jl:180-207):
+ *   the full N^4 tensor, only for N <= 256 (the engine never needs it; the reference's tests do). */
+int qlb_eri_block(qlb_basis *b, int i, int j, int k, int l, double *out);
+int qlb_eri_tensor(qlb_basis *b, double *out);
+
+/* Schwarz bounds Q_ij = sqrt(max |(mu nu|mu nu)|) as an nsh x nsh symmetric matrix (new functionality:
+ * the reference does not screen). */
+int qlb_schwarz(qlb_basis *b, double *Q);
+
+/* ---- J / K / Fock ----------------------------------------------------------------------------------------
+ * qlb_build_jk replaces contractTensorBlocksWithMatrix_CoulombLike / _ExchangeLike
+ *   (SpecialMatricesModule.jl:33-100) as called by computeMatrixCoulomb / computeMatrixExchange
+ *   (:231-244, :268-281): J[mu,nu] = sum (mu nu|la si) P[la,si], K[mu,nu] = sum (mu la|nu si) P[la,si], in ONE
+ *   fused pass over the unique, screened quartets.  Host buffers N x N; J or K may be NULL.
+ *   A quartet (ab|cd) is evaluated iff qlog(Q_ab) + qlog(Q_cd) + max qlog(|P| over the six shell blocks
+ *   ab,cd,ac,ad,bc,bd) >= qlog(tau), qlog(x) = ceil(8*log2 x): integer arithmetic, so counts are reproducible.
+ *   tau <= 0 switches screening off.
+ * qlb_fock replaces computeMatrixFock (SpecialMatricesModule.jl:284-290): F = H + 2J - K with H = T + V. */
+int qlb_build_jk(qlb_basis *b, const double *P, double tau, double *J, double *K, qlb_stats *stats);
+int qlb_fock(qlb_basis *b, const double *H, const double *P, double tau, double *F, qlb_stats *stats);
+
+/* Device-resident variant for callers that keep P/J/K in HBM (one process per GPU):
+ * dP, dJ, dK are DEVICE pointers (N x N doubles).  Only the quartet tiles owned by `rank` of `nranks` are
+ * evaluated, dJ/dK receive the rank's PARTIAL, un-symmetrised sums (J, K as defined above are obtained by
+ * summing the partials over ranks and calling qlb_symmetrize_device).  Work is enqueued on `stream`
+ * (a cudaStream_t passed as void*; NULL = the engine's own stream) and the call returns after enqueueing
+ * unless stats != NULL (stats need a synchronisation). */
+int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, double *dJ, double *dK, int rank, int nranks,
+                        void *stream, qlb_stats *stats);
+int qlb_symmetrize_device(qlb_basis *b, double *dJ, double *dK, void *stream);
+/* F = H + 2J - K elementwise on device pointers (N x N) */
+int qlb_fock_device(qlb_basis *b, const double *dH, const double *dJ, const double *dK, double *dF, void *stream);
+
+/* ---- multi-GPU (one process per GPU; NCCL over NVLink) ----------------------------------------------------
+ * qlb_comm_unique_id fills a 128-byte NCCL id on rank 0; the host broadcasts it by any means and every rank
+ * calls qlb_comm_init.  After that qlb_build_jk / qlb_fock / qlb_build_jk_device(+qlb_allreduce_jk_device)
+ * shard the quartet tiles over the ranks and combine the partial [J;K] with ONE ncclAllReduce per build. */
+int qlb_comm_unique_id(void *id128);
+int qlb_comm_init(const void *id128, int rank, int nranks);
+int qlb_comm_destroy(void);
+int qlb_allreduce_jk_device(qlb_basis *b, double *dJK /* 2*N*N contiguous */, void *stream);
+
+/* ---- one-electron matrices (SpecialMatricesModule.jl:102-177) ---------------------------- */
+int qlb_overlap(qlb_basis *b, double *S);
+int qlb_kinetic(qlb_basis *b, double *T);
+int qlb_nuclear_attraction(qlb_basis *b, int natoms, const double *xyz, const double *Z, double *V);
+
+/* ---- knobs ---------------------------------------------------------------------------------------------- */
+int qlb_set_profiling(int on); /* time every class kernel with its own event pair (serialises the classes) */
+int qlb_fp64_peak_probe(double *tflops); /* DFMA microbenchmark: the measured FP64 roofline denominator */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QLB200_H */

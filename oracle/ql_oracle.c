@@ -686,14 +686,24 @@ void orc_md_schwarz(int nsh, const double *centers, const int *L, const int *npr
 }
 
 /* The integer screening rule shared (by specification, not by code) with the CUDA path:
- *   qlog(x)   = (int) ceil( log2(x) * 8 )         (x>0; -32768 for x==0)
+ *   qlog(x)   = ceil( 8*log2(x) )  evaluated WITHOUT transcendental functions, so that CPU and GPU agree bit for
+ *               bit:  x = m*2^e with m in [1,2)  ->  8e + #{ j in 0..7 : m > 2^(j/8) }   (-32768 for x < 1e-300)
  *   keep (ab|cd)  iff  qlog(Q_ab) + qlog(Q_cd) + dlog(ab,cd) >= tlog,
- *   dlog = max over the six shell blocks ab,cd,ac,ad,bc,bd of qlog(max|P_block|), tlog = qlog(tau). */
+ *   dlog = max over the six shell blocks ab,cd,ac,ad,bc,bd of qlog(max|P_block|), tlog = qlog(tau).
+ * (New functionality: the reference does not screen) */
 int orc_qlog(double x) {
-  if (!(x > 0.0)) return -32768;
-  double v = ceil(log2(x) * 8.0);
-  if (v < -32768) v = -32768;
-  return (int)v;
+  static const double th[8] = {1.0, 1.0905077326652577, 1.189207115002721, 1.2968395546510096,
+                               1.4142135623730951, 1.5422108254079407, 1.681792830507429, 1.8340080864093424};
+  if (!(x >= 1e-300)) return -32768;
+  uint64_t bits;
+  memcpy(&bits, &x, 8);
+  int e = (int)((bits >> 52) & 0x7ff) - 1023;
+  uint64_t mb = (bits & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL;
+  double m;
+  memcpy(&m, &mb, 8);
+  int c = 0;
+  for (int j = 0; j < 8; j++) c += (m > th[j]) ? 1 : 0;
+  return 8 * e + c;
 }
 
 /* fused J+K over unique quartets with screening; J,K exactly as the reference defines them

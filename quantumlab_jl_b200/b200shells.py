@@ -1,0 +1,128 @@
+"""B200Shells -- the shell-vector type that selects the B200 backend.
+
+The reference dispatches `computeMatrixCoulomb/Exchange/Fock`, `computeTensor...` and `evaluateSCF` on the type of
+their basis argument: Vector{Shell} (native Julia), Vector{LibInt2Shell} (libint2 engine; LibInt2Module.jl:62-68).
+`B200Shells` is the third member of that family: a list of `Shell`s plus the opaque device handle (`qlb_basis`)
+that owns the device-resident shells, primitive-pair records, Schwarz bounds and class bins.  Like LibInt2Shell it
+is destroyed explicitly (`destroy()`; LibInt2Module.jl:108-110) or by the garbage collector.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import libqlb
+from .shell import Shell, flattenShells, totalBasisFunctions
+
+DEFAULT_TAU = 1e-12  # Schwarz x density threshold (protects the 1e-10 per-element parity)
+
+
+class B200Shells(list):
+    def __init__(self, shells, tau: float = DEFAULT_TAU, device: int = -1):
+        super().__init__(shells)
+        if not all(isinstance(s, Shell) for s in self):
+            raise TypeError("B200Shells takes a sequence of Shell")
+        lib = libqlb.init(device)
+        self._arrays = flattenShells(list(self))  # keep alive
+        centers, L, nprim, exps, coefs = self._arrays
+        h = C.c_void_p()
+        libqlb.check(lib.qlb_basis_create(len(self), libqlb.dptr(centers), libqlb.iptr(L), libqlb.iptr(nprim),
+                                          libqlb.dptr(exps), libqlb.dptr(coefs), C.byref(h)))
+        self._h = h
+        self.tau = float(tau)
+        self.nbf = totalBasisFunctions(list(self))
+        self.last_stats: dict | None = None
+        self._cache_P = None
+        self._cache_JK = None
+
+    # ---- handle management
+    @property
+    def handle(self):
+        if self._h is None:
+            raise libqlb.QlbError("B200Shells handle was destroyed")
+        return self._h
+
+    def destroy(self):
+        if getattr(self, "_h", None) is not None:
+            libqlb.load().qlb_basis_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    # ---- hot path
+    def _check_P(self, P) -> np.ndarray:
+        P = np.asfortranarray(P, dtype=np.float64)
+        if P.shape != (self.nbf, self.nbf):
+            raise ValueError(f"density matrix must be {self.nbf}x{self.nbf}, got {P.shape}")
+        return P
+
+    def build_jk(self, P, tau: float | None = None, want_stats: bool = True):
+        """One fused, screened pass -> (J, K) exactly as the reference defines them."""
+        P = self._check_P(P)
+        n = self.nbf
+        J = np.empty((n, n), dtype=np.float64, order="F")
+        K = np.empty((n, n), dtype=np.float64, order="F")
+        st = libqlb.Stats()
+        libqlb.check(libqlb.load().qlb_build_jk(self.handle, libqlb.dptr(P), self.tau if tau is None else tau,
+                                                libqlb.dptr(J), libqlb.dptr(K), C.byref(st) if want_stats else None))
+        if want_stats:
+            self.last_stats = st.as_dict()
+        return J, K
+
+    def jk_cached(self, P):
+        """J and K for P, computed together once: `coulomb(P)` followed by `exchange(P)` costs one pass."""
+        P = self._check_P(P)
+        if self._cache_P is None or self._cache_P.shape != P.shape or not np.array_equal(self._cache_P, P):
+            self._cache_JK = self.build_jk(P)
+            self._cache_P = P.copy()
+        return self._cache_JK
+
+    def fock(self, H, P, tau: float | None = None):
+        P = self._check_P(P)
+        H = np.asfortranarray(H, dtype=np.float64)
+        F = np.empty_like(P, order="F")
+        st = libqlb.Stats()
+        libqlb.check(libqlb.load().qlb_fock(self.handle, libqlb.dptr(H), libqlb.dptr(P), self.tau if tau is None else tau,
+                                            libqlb.dptr(F), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return F
+
+    def schwarz(self) -> np.ndarray:
+        Q = np.zeros((len(self), len(self)), dtype=np.float64, order="F")
+        libqlb.check(libqlb.load().qlb_schwarz(self.handle, libqlb.dptr(Q)))
+        return Q
+
+    def eri_tensor(self) -> np.ndarray:
+        n = self.nbf
+        out = np.empty((n, n, n, n), dtype=np.float64, order="F")
+        libqlb.check(libqlb.load().qlb_eri_tensor(self.handle, libqlb.dptr(out)))
+        return out
+
+    def eri_block(self, i: int, j: int, k: int, l: int) -> np.ndarray:
+        from .shell import nbf
+
+        shp = tuple(nbf(self[s]) for s in (i, j, k, l))
+        out = np.empty(shp, dtype=np.float64, order="F")
+        libqlb.check(libqlb.load().qlb_eri_block(self.handle, i, j, k, l, libqlb.dptr(out)))
+        return out
+
+    def one_electron(self, which: str, geometry=None) -> np.ndarray:
+        n = self.nbf
+        out = np.empty((n, n), dtype=np.float64, order="F")
+        lib = libqlb.load()
+        if which == "overlap":
+            libqlb.check(lib.qlb_overlap(self.handle, libqlb.dptr(out)))
+        elif which == "kinetic":
+            libqlb.check(lib.qlb_kinetic(self.handle, libqlb.dptr(out)))
+        elif which == "nuclear":
+            xyz = np.ascontiguousarray([a.position for a in geometry.atoms], dtype=np.float64).reshape(-1)
+            Z = np.ascontiguousarray([a.element.atomicNumber for a in geometry.atoms], dtype=np.float64)
+            libqlb.check(lib.qlb_nuclear_attraction(self.handle, Z.size, libqlb.dptr(xyz), libqlb.dptr(Z), libqlb.dptr(out)))
+        else:
+            raise ValueError(which)
+        return out

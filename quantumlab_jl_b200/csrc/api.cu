@@ -1,0 +1,829 @@
+// api.cu -- the C ABI of libqlb200.so (see include/qlb200.h) and the host-side orchestration of the Fock build:
+// pair lists, class bins, screening prefixes, kernel launches, statistics.  No CPU compute path exists here.
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+
+#include "qlb_internal.h"
+
+namespace qlb {
+
+static thread_local std::string g_err;
+static Engine g_engine;
+Engine &engine() { return g_engine; }
+void set_error(const std::string &msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char *what) {
+  set_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what);
+  return QLB_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ Boys table (host, long double series)
+static void make_boys_table(std::vector<double> &tab) {
+  tab.assign((size_t)BOYS_NROW * BOYS_NCOL, 0.0);
+  for (int i = 0; i < BOYS_NROW; ++i) {
+    const long double T = (long double)i * (long double)BOYS_DT;
+    const int mtop = BOYS_NCOL - 1;
+    // F_mtop(T) = exp(-T) sum_k (2T)^k / ((2m+1)(2m+3)...(2m+2k+1)), then downward recursion
+    long double term = 1.0L / (2 * mtop + 1), sum = term;
+    for (int k = 1; k < 2000; ++k) {
+      term *= 2.0L * T / (2 * mtop + 2 * k + 1);
+      sum += term;
+      if (term < 1e-22L * sum) break;
+    }
+    const long double ex = expl(-T);
+    long double F = ex * sum;
+    tab[(size_t)i * BOYS_NCOL + mtop] = (double)F;
+    for (int m = mtop; m > 0; --m) {
+      F = (2.0L * T * F + ex) / (2 * m - 1);
+      tab[(size_t)i * BOYS_NCOL + m - 1] = (double)F;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ small kernels
+// K1: primitive-pair records, one warp per shell pair, lanes stride the na*nb primitive pairs (coalesced SoA writes)
+__global__ void pair_prim_kernel(int npairs, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
+                                 const int *__restrict__ pair_poff, const double *__restrict__ xyz,
+                                 const int *__restrict__ poff, const double *__restrict__ exps,
+                                 const double *__restrict__ coefs, double *pp_p, double *pp_x, double *pp_y, double *pp_z,
+                                 double *pp_k) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= npairs) return;
+  const int a = pair_a[w], b = pair_b[w];
+  const int oa = poff[a], ob = poff[b], na = poff[a + 1] - oa, nb = poff[b + 1] - ob;
+  const double Ax = xyz[3 * a], Ay = xyz[3 * a + 1], Az = xyz[3 * a + 2];
+  const double Bx = xyz[3 * b], By = xyz[3 * b + 1], Bz = xyz[3 * b + 2];
+  const double ab2 = (Ax - Bx) * (Ax - Bx) + (Ay - By) * (Ay - By) + (Az - Bz) * (Az - Bz);
+  const int base = pair_poff[w];
+  for (int t = lane; t < na * nb; t += 32) {
+    const int ia = t / nb, ib = t - ia * nb;
+    const double al = exps[oa + ia], be = exps[ob + ib];
+    const double p = al + be, ip = 1.0 / p;
+    pp_p[base + t] = p;
+    pp_x[base + t] = (al * Ax + be * Bx) * ip;
+    pp_y[base + t] = (al * Ay + be * By) * ip;
+    pp_z[base + t] = (al * Az + be * Bz) * ip;
+    pp_k[base + t] = coefs[oa + ia] * coefs[ob + ib] * exp(-al * be * ip * ab2);
+  }
+}
+
+// K3a: dl[i + nsh*j] = qlog(max |P| over shell block (i,j)); dl[nsh*nsh] = global max
+__global__ void density_block_max_kernel(int nsh, int N, const int *__restrict__ boff, const double *__restrict__ P, int *dl) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int q = -32768;
+  if (idx < nsh * nsh) {
+    const int i = idx % nsh, j = idx / nsh;
+    double m = 0.0;
+    for (int c = boff[j]; c < boff[j + 1]; ++c)
+      for (int r = boff[i]; r < boff[i + 1]; ++r) m = fmax(m, fabs(P[r + (size_t)N * c]));
+    q = qlog_exact(m);
+    dl[idx] = q;
+  }
+  q = __reduce_max_sync(0xffffffffu, q);
+  if ((threadIdx.x & 31) == 0) atomicMax(dl + nsh * nsh, q);
+}
+
+__global__ void symmetrize_kernel(int N, double *A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i < N && j < i) {
+    const double v = 0.5 * (A[i + (size_t)N * j] + A[j + (size_t)N * i]);
+    A[i + (size_t)N * j] = v;
+    A[j + (size_t)N * i] = v;
+  }
+}
+
+// K6: F = H + 2J - K  (SpecialMatricesModule.jl:289)
+__global__ void fock_kernel(size_t n, const double *__restrict__ H, const double *__restrict__ J,
+                            const double *__restrict__ K, double *F) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) F[i] = H[i] + 2.0 * J[i] - K[i];
+}
+
+__global__ void dfma_probe_kernel(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+static int require_ready() {
+  if (!g_engine.ready) {
+    set_error("qlb_init has not been called (or failed): no CUDA device, no compute -- there is no CPU fallback");
+    return QLB_ERR_STATE;
+  }
+  return QLB_OK;
+}
+
+template <class T>
+static int upload(T **dptr, const std::vector<T> &h) {
+  QLB_CUDA(cudaMalloc((void **)dptr, std::max<size_t>(h.size(), 1) * sizeof(T)));
+  if (!h.empty()) QLB_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return QLB_OK;
+}
+
+static void fill_pp(const qlb_basis *b, PrimPairs &pp) {
+  pp.p = b->d_pp[0]; pp.x = b->d_pp[1]; pp.y = b->d_pp[2]; pp.z = b->d_pp[3]; pp.k = b->d_pp[4];
+}
+
+static int run_pair_prims(qlb_basis *b) {
+  Engine &e = g_engine;
+  const int np = (int)b->npairs;
+  if (np == 0) return QLB_OK;
+  const int threads = 256, blocks = (int)(((int64_t)np * 32 + threads - 1) / threads);
+  pair_prim_kernel<<<blocks, threads, 0, e.stream>>>(np, b->d_pair_a, b->d_pair_b, b->d_pair_poff, b->d_xyz, b->d_poff,
+                                                     b->d_exps, b->d_coefs, b->d_pp[0], b->d_pp[1], b->d_pp[2], b->d_pp[3],
+                                                     b->d_pp[4]);
+  QLB_CUDA(cudaGetLastError());
+  return QLB_OK;
+}
+
+static void compute_pair_offsets(qlb_basis *b) {
+  b->h_pair_poff.resize(b->npairs + 1);
+  int64_t off = 0;
+  for (int64_t i = 0; i < b->npairs; ++i) {
+    b->h_pair_poff[i] = (int)off;
+    off += (int64_t)b->h_nprim[b->h_pair_a[i]] * b->h_nprim[b->h_pair_b[i]];
+  }
+  b->h_pair_poff[b->npairs] = (int)off;
+  b->nprimpairs = off;
+}
+
+}  // namespace qlb
+
+using namespace qlb;
+
+// =================================================================== lifetime
+extern "C" int qlb_init(int device) {
+  Engine &e = g_engine;
+  if (e.ready) return QLB_OK;
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0) {
+    set_error(std::string("no CUDA device available (") + cudaGetErrorString(err) +
+              "): libqlb200 has no CPU fallback");
+    return QLB_ERR_CUDA;
+  }
+  if (device < 0) QLB_CUDA(cudaGetDevice(&device));
+  if (device >= ndev) {
+    set_error("device index out of range");
+    return QLB_ERR_ARG;
+  }
+  QLB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  QLB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_error(std::string("device ") + prop.name + " is not sm_100-class; libqlb200 ships sm_100a code only");
+    return QLB_ERR_CUDA;
+  }
+  e.device = device;
+  e.sm_count = prop.multiProcessorCount;
+  QLB_CUDA(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
+  std::vector<double> tab;
+  make_boys_table(tab);
+  QLB_CUDA(cudaMalloc((void **)&e.d_boys, tab.size() * sizeof(double)));
+  QLB_CUDA(cudaMemcpy(e.d_boys, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+  // the rolled high-L kernels keep their intermediates in local memory
+  cudaDeviceSetLimit(cudaLimitStackSize, 20 * 1024);
+  e.ready = true;
+  return QLB_OK;
+}
+
+extern "C" int qlb_finalize(void) {
+  Engine &e = g_engine;
+  if (!e.ready) return QLB_OK;
+  qlb_comm_destroy();
+  cudaSetDevice(e.device);
+  if (e.d_boys) cudaFree(e.d_boys);
+  if (e.stream) cudaStreamDestroy(e.stream);
+  e = Engine();
+  return QLB_OK;
+}
+
+extern "C" const char *qlb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int qlb_device_info(char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor) {
+  if (int rc = require_ready()) return rc;
+  cudaDeviceProp prop;
+  QLB_CUDA(cudaGetDeviceProperties(&prop, g_engine.device));
+  if (name && name_len > 0) {
+    strncpy(name, prop.name, name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return QLB_OK;
+}
+
+extern "C" int qlb_set_profiling(int on) {
+  g_engine.profiling = on != 0;
+  return QLB_OK;
+}
+
+extern "C" int qlb_fp64_peak_probe(double *tflops) {
+  if (int rc = require_ready()) return rc;
+  Engine &e = g_engine;
+  QLB_CUDA(cudaSetDevice(e.device));
+  const int blocks = e.sm_count * 8, threads = 256, iters = 1 << 15;
+  double *d = nullptr;
+  QLB_CUDA(cudaMalloc((void **)&d, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  dfma_probe_kernel<<<blocks, threads, 0, e.stream>>>(d, 1024);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(a, e.stream);
+    dfma_probe_kernel<<<blocks, threads, 0, e.stream>>>(d, iters);
+    cudaEventRecord(b, e.stream);
+    QLB_CUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    best = std::max(best, fl / (ms * 1e-3) * 1e-12);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  if (tflops) *tflops = best;
+  return QLB_OK;
+}
+
+// =================================================================== basis
+extern "C" int qlb_basis_destroy(qlb_basis *b) {
+  if (!b) return QLB_OK;
+  if (g_engine.ready) cudaSetDevice(g_engine.device);
+  void *ptrs[] = {b->d_xyz, b->d_exps, b->d_coefs, b->d_poff, b->d_boff, b->d_L, b->d_pair_a, b->d_pair_b,
+                  b->d_pair_poff, b->d_pair_ql, b->d_pair_Q, b->d_pp[0], b->d_pp[1], b->d_pp[2], b->d_pp[3], b->d_pp[4],
+                  b->d_P, b->d_JK, b->d_H, b->d_dl, b->d_counters};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  for (auto &ev : b->ev)
+    if (ev) cudaEventDestroy(ev);
+  delete b;
+  return QLB_OK;
+}
+
+static int basis_build_pairs(qlb_basis *b) {
+  Engine &e = g_engine;
+  const int nsh = b->nsh;
+  // enumerate unique pairs, canonical orientation la >= lb, bucketed by class in (i,j) order
+  std::vector<int> pa[NCLASS], pb[NCLASS];
+  for (int i = 0; i < nsh; ++i)
+    for (int j = 0; j <= i; ++j) {
+      int a = i, c = j;
+      if (b->h_L[a] < b->h_L[c]) std::swap(a, c);
+      const int cls = class_of(b->h_L[a], b->h_L[c]);
+      pa[cls].push_back(a);
+      pb[cls].push_back(c);
+    }
+  b->h_pair_a.clear();
+  b->h_pair_b.clear();
+  b->class_off[0] = 0;
+  for (int c = 0; c < NCLASS; ++c) {
+    b->h_pair_a.insert(b->h_pair_a.end(), pa[c].begin(), pa[c].end());
+    b->h_pair_b.insert(b->h_pair_b.end(), pb[c].begin(), pb[c].end());
+    b->class_off[c + 1] = (int)b->h_pair_a.size();
+  }
+  b->npairs = (int64_t)b->h_pair_a.size();
+  compute_pair_offsets(b);
+  if (b->nprimpairs > 0x7fffffff) {
+    set_error("too many primitive pairs for 32-bit offsets");
+    return QLB_ERR_ARG;
+  }
+  if (int rc = upload(&b->d_pair_a, b->h_pair_a)) return rc;
+  if (int rc = upload(&b->d_pair_b, b->h_pair_b)) return rc;
+  if (int rc = upload(&b->d_pair_poff, b->h_pair_poff)) return rc;
+  for (int k = 0; k < 5; ++k) QLB_CUDA(cudaMalloc((void **)&b->d_pp[k], std::max<int64_t>(b->nprimpairs, 1) * sizeof(double)));
+  QLB_CUDA(cudaMalloc((void **)&b->d_pair_Q, std::max<int64_t>(b->npairs, 1) * sizeof(double)));
+  QLB_CUDA(cudaMalloc((void **)&b->d_pair_ql, std::max<int64_t>(b->npairs, 1) * sizeof(int)));
+  if (int rc = run_pair_prims(b)) return rc;
+  // K2: Schwarz bounds per pair
+  SchwarzParams sp;
+  sp.sh_xyz = b->d_xyz; sp.pair_a = b->d_pair_a; sp.pair_b = b->d_pair_b; sp.pair_poff = b->d_pair_poff;
+  fill_pp(b, sp.pp);
+  sp.boys = e.d_boys; sp.Q = b->d_pair_Q;
+  for (int c = 0; c < NCLASS; ++c) {
+    sp.off = b->class_off[c];
+    sp.n = b->class_off[c + 1] - b->class_off[c];
+    if (sp.n == 0) continue;
+    if (int ce = launch_schwarz_kernel(c, (unsigned)((sp.n + 63) / 64), e.stream, sp)) return cuda_fail((cudaError_t)ce, "schwarz_kernel");
+  }
+  b->h_pair_Q.resize(b->npairs);
+  QLB_CUDA(cudaMemcpyAsync(b->h_pair_Q.data(), b->d_pair_Q, b->npairs * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  QLB_CUDA(cudaStreamSynchronize(e.stream));
+  // K3 (host part): sort each class by bound, descending; ties by original position (deterministic)
+  std::vector<int> perm(b->npairs);
+  std::iota(perm.begin(), perm.end(), 0);
+  for (int c = 0; c < NCLASS; ++c)
+    std::stable_sort(perm.begin() + b->class_off[c], perm.begin() + b->class_off[c + 1],
+                     [&](int x, int y) { return b->h_pair_Q[x] > b->h_pair_Q[y]; });
+  std::vector<int> na(b->npairs), nb(b->npairs);
+  std::vector<double> nq(b->npairs);
+  b->h_pair_ql.resize(b->npairs);
+  b->qlmax = -32768;
+  for (int64_t i = 0; i < b->npairs; ++i) {
+    na[i] = b->h_pair_a[perm[i]];
+    nb[i] = b->h_pair_b[perm[i]];
+    nq[i] = b->h_pair_Q[perm[i]];
+    b->h_pair_ql[i] = qlog_exact(nq[i]);
+    b->qlmax = std::max(b->qlmax, b->h_pair_ql[i]);
+  }
+  b->h_pair_a.swap(na);
+  b->h_pair_b.swap(nb);
+  b->h_pair_Q.swap(nq);
+  compute_pair_offsets(b);
+  QLB_CUDA(cudaMemcpy(b->d_pair_a, b->h_pair_a.data(), b->npairs * sizeof(int), cudaMemcpyHostToDevice));
+  QLB_CUDA(cudaMemcpy(b->d_pair_b, b->h_pair_b.data(), b->npairs * sizeof(int), cudaMemcpyHostToDevice));
+  QLB_CUDA(cudaMemcpy(b->d_pair_poff, b->h_pair_poff.data(), (b->npairs + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  QLB_CUDA(cudaMemcpy(b->d_pair_ql, b->h_pair_ql.data(), b->npairs * sizeof(int), cudaMemcpyHostToDevice));
+  QLB_CUDA(cudaMemcpy(b->d_pair_Q, b->h_pair_Q.data(), b->npairs * sizeof(double), cudaMemcpyHostToDevice));
+  if (int rc = run_pair_prims(b)) return rc;
+  QLB_CUDA(cudaStreamSynchronize(e.stream));
+  return QLB_OK;
+}
+
+extern "C" int qlb_basis_create(int nsh, const double *centers, const int32_t *L, const int32_t *nprim,
+                                const double *exps, const double *coefs, qlb_basis **out) {
+  if (int rc = require_ready()) return rc;
+  if (!out || nsh <= 0 || !centers || !L || !nprim || !exps || !coefs) {
+    set_error("qlb_basis_create: null pointer or nsh <= 0");
+    return QLB_ERR_ARG;
+  }
+  QLB_CUDA(cudaSetDevice(g_engine.device));
+  qlb_basis *b = new qlb_basis();
+  b->nsh = nsh;
+  b->h_xyz.assign(centers, centers + 3 * (size_t)nsh);
+  b->h_L.assign(L, L + nsh);
+  b->h_nprim.assign(nprim, nprim + nsh);
+  b->h_poff.resize(nsh + 1);
+  b->h_boff.resize(nsh + 1);
+  b->h_poff[0] = b->h_boff[0] = 0;
+  for (int i = 0; i < nsh; ++i) {
+    if (L[i] < 0 || L[i] > QLB_MAX_L) {
+      // the reference performs the analogous check against MAX_AM on the Julia side (LibInt2Module.jl:79-83)
+      set_error("qlb_basis_create: shell angular momentum outside 0..QLB_MAX_L");
+      delete b;
+      return QLB_ERR_ARG;
+    }
+    if (nprim[i] <= 0) {
+      set_error("qlb_basis_create: shell without primitives");
+      delete b;
+      return QLB_ERR_ARG;
+    }
+    b->h_poff[i + 1] = b->h_poff[i] + nprim[i];
+    b->h_boff[i + 1] = b->h_boff[i] + ncart(L[i]);
+  }
+  b->nprim_total = b->h_poff[nsh];
+  b->nbf = b->h_boff[nsh];
+  b->h_exps.assign(exps, exps + b->nprim_total);
+  b->h_coefs.assign(coefs, coefs + b->nprim_total);
+  int rc = QLB_OK;
+  if ((rc = upload(&b->d_xyz, b->h_xyz)) || (rc = upload(&b->d_exps, b->h_exps)) || (rc = upload(&b->d_coefs, b->h_coefs)) ||
+      (rc = upload(&b->d_poff, b->h_poff)) || (rc = upload(&b->d_boff, b->h_boff)) || (rc = upload(&b->d_L, b->h_L))) {
+    qlb_basis_destroy(b);
+    return rc;
+  }
+  const size_t N2 = (size_t)b->nbf * b->nbf;
+  cudaError_t ce;
+  if ((ce = cudaMalloc((void **)&b->d_P, N2 * sizeof(double))) != cudaSuccess ||
+      (ce = cudaMalloc((void **)&b->d_JK, 2 * N2 * sizeof(double))) != cudaSuccess ||
+      (ce = cudaMalloc((void **)&b->d_H, N2 * sizeof(double))) != cudaSuccess ||
+      (ce = cudaMalloc((void **)&b->d_dl, ((size_t)nsh * nsh + 1) * sizeof(int))) != cudaSuccess ||
+      (ce = cudaMalloc((void **)&b->d_counters, 2 * NQCLASS * sizeof(unsigned long long))) != cudaSuccess) {
+    qlb_basis_destroy(b);
+    return cuda_fail(ce, "cudaMalloc(scratch)");
+  }
+  for (auto &ev : b->ev) cudaEventCreate(&ev);
+  if ((rc = basis_build_pairs(b))) {
+    qlb_basis_destroy(b);
+    return rc;
+  }
+  *out = b;
+  return QLB_OK;
+}
+
+extern "C" int qlb_basis_nbf(const qlb_basis *b, int *nbf) {
+  if (!b || !nbf) return QLB_ERR_ARG;
+  *nbf = b->nbf;
+  return QLB_OK;
+}
+extern "C" int qlb_basis_npairs(const qlb_basis *b, int64_t *npairs) {
+  if (!b || !npairs) return QLB_ERR_ARG;
+  *npairs = b->npairs;
+  return QLB_OK;
+}
+
+extern "C" int qlb_schwarz(qlb_basis *b, double *Q) {
+  if (int rc = require_ready()) return rc;
+  if (!b || !Q) return QLB_ERR_ARG;
+  const int n = b->nsh;
+  for (int64_t i = 0; i < b->npairs; ++i) {
+    const int a = b->h_pair_a[i], c = b->h_pair_b[i];
+    Q[a + (size_t)n * c] = Q[c + (size_t)n * a] = b->h_pair_Q[i];
+  }
+  return QLB_OK;
+}
+
+// =================================================================== J/K
+static void base_params(qlb_basis *b, ClassParams &prm) {
+  memset(&prm, 0, sizeof(prm));
+  prm.sh_xyz = b->d_xyz; prm.sh_boff = b->d_boff; prm.nsh = b->nsh; prm.nbf = b->nbf;
+  prm.pair_a = b->d_pair_a; prm.pair_b = b->d_pair_b; prm.pair_poff = b->d_pair_poff; prm.pair_ql = b->d_pair_ql;
+  fill_pp(b, prm.pp);
+  prm.boys = g_engine.d_boys;
+  prm.dl = b->d_dl;
+  prm.nranks = 1;
+}
+
+// number of leading pairs of class c (sorted by bound, descending) with ql >= need
+static int prefix_count(const qlb_basis *b, int c, int need) {
+  const int *lo = b->h_pair_ql.data() + b->class_off[c], *hi = b->h_pair_ql.data() + b->class_off[c + 1];
+  // descending order: first position with ql < need
+  return (int)(std::partition_point(lo, hi, [need](int q) { return q >= need; }) - lo);
+}
+
+extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, double *dJ, double *dK, int rank,
+                                   int nranks, void *stream_, qlb_stats *stats) {
+  if (int rc = require_ready()) return rc;
+  if (!b || !dP || !dJ || !dK || nranks < 1 || rank < 0 || rank >= nranks) {
+    set_error("qlb_build_jk_device: bad argument");
+    return QLB_ERR_ARG;
+  }
+  Engine &e = g_engine;
+  QLB_CUDA(cudaSetDevice(e.device));
+  cudaStream_t s = stream_ ? (cudaStream_t)stream_ : e.stream;
+  const int nsh = b->nsh, N = b->nbf;
+  const size_t N2 = (size_t)N * N;
+  const bool screen = tau > 0.0;
+  const bool prof = e.profiling && stats;
+  int launches = 0;
+  if (stats) cudaEventRecord(b->ev[0], s);
+  int dlmax = 0, tlog = -32768;
+  if (screen) {
+    const int init = -32768;
+    QLB_CUDA(cudaMemcpyAsync(b->d_dl + (size_t)nsh * nsh, &init, sizeof(int), cudaMemcpyHostToDevice, s));
+    const int threads = 128, blocks = (nsh * nsh + threads - 1) / threads;
+    density_block_max_kernel<<<blocks, threads, 0, s>>>(nsh, N, b->d_boff, dP, b->d_dl);
+    QLB_CUDA(cudaGetLastError());
+    ++launches;
+    QLB_CUDA(cudaMemcpyAsync(&dlmax, b->d_dl + (size_t)nsh * nsh, sizeof(int), cudaMemcpyDeviceToHost, s));
+    QLB_CUDA(cudaStreamSynchronize(s));
+    tlog = qlog_exact(tau);
+  }
+  QLB_CUDA(cudaMemsetAsync(dJ, 0, N2 * sizeof(double), s));
+  QLB_CUDA(cudaMemsetAsync(dK, 0, N2 * sizeof(double), s));
+  QLB_CUDA(cudaMemsetAsync(b->d_counters, 0, 2 * NQCLASS * sizeof(unsigned long long), s));
+  int nsig[NCLASS];
+  int64_t pairs_sig = 0;
+  for (int c = 0; c < NCLASS; ++c) {
+    nsig[c] = screen ? prefix_count(b, c, tlog - b->qlmax - dlmax) : b->class_off[c + 1] - b->class_off[c];
+    pairs_sig += nsig[c];
+  }
+  ClassParams prm;
+  base_params(b, prm);
+  prm.tlog = tlog; prm.dlmax = dlmax; prm.screen = screen ? 1 : 0;
+  prm.rank = rank; prm.nranks = nranks;
+  prm.P = dP; prm.J = dJ; prm.K = dK;
+  if (stats) cudaEventRecord(b->ev[1], s);
+  for (int X = NCLASS - 1; X >= 0; --X)  // heaviest classes first
+    for (int Y = X; Y >= 0; --Y) {
+      const int qc = qclass_of(X, Y);
+      if (nsig[X] == 0 || nsig[Y] == 0) continue;
+      prm.bra_off = b->class_off[X]; prm.bra_n = nsig[X];
+      prm.ket_off = b->class_off[Y]; prm.ket_n = nsig[Y];
+      prm.same = (X == Y) ? 1 : 0;
+      int ket_eff = nsig[Y];
+      if (screen) ket_eff = std::min(ket_eff, prefix_count(b, Y, tlog - dlmax - b->h_pair_ql[b->class_off[X]]));
+      if (ket_eff == 0) continue;
+      const int nrows = (prm.bra_n + TILE_BRA - 1) / TILE_BRA;
+      const int nrows_local = rank < nrows ? (nrows - rank + nranks - 1) / nranks : 0;
+      if (nrows_local == 0) continue;
+      prm.nbx = (ket_eff + TILE_KET - 1) / TILE_KET;
+      const int64_t grid = (int64_t)nrows_local * prm.nbx;
+      if (grid > 0x7fffffffLL) {
+        set_error("qlb_build_jk_device: grid too large");
+        return QLB_ERR_ARG;
+      }
+      prm.counters = b->d_counters + 2 * qc;
+      if (prof) cudaEventRecord(b->ev[4 + 2 * qc], s);
+      if (int ce = launch_class_kernel(X, Y, 0, (unsigned)grid, s, prm)) return cuda_fail((cudaError_t)ce, "eri_class_kernel");
+      if (prof) cudaEventRecord(b->ev[4 + 2 * qc + 1], s);
+      ++launches;
+    }
+  if (stats) {
+    cudaEventRecord(b->ev[2], s);
+    unsigned long long h[2 * NQCLASS];
+    QLB_CUDA(cudaMemcpyAsync(h, b->d_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
+    QLB_CUDA(cudaStreamSynchronize(s));
+    memset(stats, 0, sizeof(*stats));
+    stats->quartets_unique = b->npairs * (b->npairs + 1) / 2;
+    stats->pairs_total = b->npairs;
+    stats->pairs_significant = pairs_sig;
+    stats->kernel_launches = launches;
+    for (int X = 0; X < NCLASS; ++X)
+      for (int Y = 0; Y <= X; ++Y) {
+        const int qc = qclass_of(X, Y);
+        stats->quartets_kept_class[qc] = (int64_t)h[2 * qc];
+        stats->prim_quartets_class[qc] = (int64_t)h[2 * qc + 1];
+        stats->quartets_kept += (int64_t)h[2 * qc];
+        double fp, fd;
+        class_flops(X, Y, fp, fd);
+        stats->flops_algorithmic += fp * (double)h[2 * qc + 1] + fd * (double)h[2 * qc];
+        if (prof && h[2 * qc]) {
+          float ms = 0;
+          if (cudaEventElapsedTime(&ms, b->ev[4 + 2 * qc], b->ev[4 + 2 * qc + 1]) == cudaSuccess) stats->ms_class[qc] = ms;
+        }
+      }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, b->ev[0], b->ev[2]);
+    stats->ms_total = ms;
+    cudaEventElapsedTime(&ms, b->ev[1], b->ev[2]);
+    stats->ms_eri = ms;
+  }
+  return QLB_OK;
+}
+
+extern "C" int qlb_symmetrize_device(qlb_basis *b, double *dJ, double *dK, void *stream_) {
+  if (int rc = require_ready()) return rc;
+  if (!b) return QLB_ERR_ARG;
+  cudaStream_t s = stream_ ? (cudaStream_t)stream_ : g_engine.stream;
+  const int N = b->nbf;
+  dim3 block(32, 8), grid((N + 31) / 32, (N + 7) / 8);
+  if (dJ) symmetrize_kernel<<<grid, block, 0, s>>>(N, dJ);
+  if (dK) symmetrize_kernel<<<grid, block, 0, s>>>(N, dK);
+  QLB_CUDA(cudaGetLastError());
+  return QLB_OK;
+}
+
+extern "C" int qlb_fock_device(qlb_basis *b, const double *dH, const double *dJ, const double *dK, double *dF, void *stream_) {
+  if (int rc = require_ready()) return rc;
+  if (!b || !dH || !dJ || !dK || !dF) return QLB_ERR_ARG;
+  cudaStream_t s = stream_ ? (cudaStream_t)stream_ : g_engine.stream;
+  const size_t n = (size_t)b->nbf * b->nbf;
+  fock_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, dH, dJ, dK, dF);
+  QLB_CUDA(cudaGetLastError());
+  return QLB_OK;
+}
+
+// shared host-buffer path: P up, fused J/K (sharded + all-reduced when a communicator exists), symmetrise
+static int jk_host_common(qlb_basis *b, const double *P, double tau, qlb_stats *stats) {
+  Engine &e = g_engine;
+  const size_t N2 = (size_t)b->nbf * b->nbf;
+  QLB_CUDA(cudaSetDevice(e.device));
+  QLB_CUDA(cudaMemcpyAsync(b->d_P, P, N2 * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  if (int rc = qlb_build_jk_device(b, b->d_P, tau, b->d_JK, b->d_JK + N2, e.rank, e.nranks, e.stream, stats)) return rc;
+  if (e.nranks > 1)
+    if (int rc = qlb_allreduce_jk_device(b, b->d_JK, e.stream)) return rc;
+  if (int rc = qlb_symmetrize_device(b, b->d_JK, b->d_JK + N2, e.stream)) return rc;
+  if (stats) stats->kernel_launches += 2;
+  return QLB_OK;
+}
+
+extern "C" int qlb_build_jk(qlb_basis *b, const double *P, double tau, double *J, double *K, qlb_stats *stats) {
+  if (int rc = require_ready()) return rc;
+  if (!b || !P || (!J && !K)) {
+    set_error("qlb_build_jk: null pointer");
+    return QLB_ERR_ARG;
+  }
+  Engine &e = g_engine;
+  const size_t N2 = (size_t)b->nbf * b->nbf;
+  if (int rc = jk_host_common(b, P, tau, stats)) return rc;
+  if (J) QLB_CUDA(cudaMemcpyAsync(J, b->d_JK, N2 * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  if (K) QLB_CUDA(cudaMemcpyAsync(K, b->d_JK + N2, N2 * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  QLB_CUDA(cudaStreamSynchronize(e.stream));
+  return QLB_OK;
+}
+
+extern "C" int qlb_fock(qlb_basis *b, const double *H, const double *P, double tau, double *F, qlb_stats *stats) {
+  if (int rc = require_ready()) return rc;
+  if (!b || !H || !P || !F) {
+    set_error("qlb_fock: null pointer");
+    return QLB_ERR_ARG;
+  }
+  Engine &e = g_engine;
+  const size_t N2 = (size_t)b->nbf * b->nbf;
+  QLB_CUDA(cudaSetDevice(e.device));
+  QLB_CUDA(cudaMemcpyAsync(b->d_H, H, N2 * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  if (int rc = jk_host_common(b, P, tau, stats)) return rc;
+  // F overwrites the P scratch (P is no longer needed)
+  if (int rc = qlb_fock_device(b, b->d_H, b->d_JK, b->d_JK + N2, b->d_P, e.stream)) return rc;
+  if (stats) stats->kernel_launches += 1;
+  QLB_CUDA(cudaMemcpyAsync(F, b->d_P, N2 * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  QLB_CUDA(cudaStreamSynchronize(e.stream));
+  return QLB_OK;
+}
+
+// =================================================================== ERI tensor / block
+static int tensor_device(qlb_basis *b, double *dT) {
+  Engine &e = g_engine;
+  const size_t N = b->nbf;
+  QLB_CUDA(cudaMemsetAsync(dT, 0, N * N * N * N * sizeof(double), e.stream));
+  ClassParams prm;
+  base_params(b, prm);
+  prm.tensor = dT;
+  for (int X = 0; X < NCLASS; ++X)
+    for (int Y = 0; Y <= X; ++Y) {
+      prm.bra_off = b->class_off[X]; prm.bra_n = b->class_off[X + 1] - b->class_off[X];
+      prm.ket_off = b->class_off[Y]; prm.ket_n = b->class_off[Y + 1] - b->class_off[Y];
+      if (prm.bra_n == 0 || prm.ket_n == 0) continue;
+      prm.same = (X == Y) ? 1 : 0;
+      prm.nbx = (prm.ket_n + TILE_KET - 1) / TILE_KET;
+      const int64_t grid = (int64_t)((prm.bra_n + TILE_BRA - 1) / TILE_BRA) * prm.nbx;
+      if (int ce = launch_class_kernel(X, Y, 1, (unsigned)grid, e.stream, prm)) return cuda_fail((cudaError_t)ce, "eri_class_kernel(tensor)");
+    }
+  return QLB_OK;
+}
+
+extern "C" int qlb_eri_tensor(qlb_basis *b, double *out) {
+  if (int rc = require_ready()) return rc;
+  if (!b || !out) return QLB_ERR_ARG;
+  if (b->nbf > 160) {
+    set_error("qlb_eri_tensor: N > 160; the N^4 tensor is only materialised for test-sized systems");
+    return QLB_ERR_ARG;
+  }
+  Engine &e = g_engine;
+  QLB_CUDA(cudaSetDevice(e.device));
+  const size_t N = b->nbf, n4 = N * N * N * N;
+  double *dT = nullptr;
+  QLB_CUDA(cudaMalloc((void **)&dT, n4 * sizeof(double)));
+  int rc = tensor_device(b, dT);
+  if (rc == QLB_OK) {
+    cudaError_t ce = cudaMemcpyAsync(out, dT, n4 * sizeof(double), cudaMemcpyDeviceToHost, e.stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e.stream);
+    if (ce != cudaSuccess) rc = cuda_fail(ce, "tensor D2H");
+  }
+  cudaFree(dT);
+  return rc;
+}
+
+extern "C" int qlb_eri_block(qlb_basis *b, int i, int j, int k, int l, double *out) {
+  if (int rc = require_ready()) return rc;
+  if (!b || !out) return QLB_ERR_ARG;
+  const int idx[4] = {i, j, k, l};
+  for (int s = 0; s < 4; ++s)
+    if (idx[s] < 0 || idx[s] >= b->nsh) {
+      set_error("qlb_eri_block: shell index out of range");
+      return QLB_ERR_ARG;
+    }
+  // a four-shell sub-basis; its full tensor contains the requested block
+  std::vector<double> xyz, ex, co;
+  std::vector<int32_t> L, np;
+  for (int s = 0; s < 4; ++s) {
+    const int sh = idx[s];
+    xyz.insert(xyz.end(), b->h_xyz.begin() + 3 * sh, b->h_xyz.begin() + 3 * sh + 3);
+    L.push_back(b->h_L[sh]);
+    np.push_back(b->h_nprim[sh]);
+    ex.insert(ex.end(), b->h_exps.begin() + b->h_poff[sh], b->h_exps.begin() + b->h_poff[sh + 1]);
+    co.insert(co.end(), b->h_coefs.begin() + b->h_poff[sh], b->h_coefs.begin() + b->h_poff[sh + 1]);
+  }
+  qlb_basis *mini = nullptr;
+  if (int rc = qlb_basis_create(4, xyz.data(), L.data(), np.data(), ex.data(), co.data(), &mini)) return rc;
+  const size_t n = mini->nbf;
+  std::vector<double> T(n * n * n * n);
+  int rc = qlb_eri_tensor(mini, T.data());
+  if (rc == QLB_OK) {
+    const int nA = ncart(L[0]), nB = ncart(L[1]), nC = ncart(L[2]), nD = ncart(L[3]);
+    const int *bo = mini->h_boff.data();
+    for (int d = 0; d < nD; ++d)
+      for (int c = 0; c < nC; ++c)
+        for (int bb = 0; bb < nB; ++bb)
+          for (int a = 0; a < nA; ++a)
+            out[a + nA * (bb + nB * (c + nC * d))] = T[(bo[0] + a) + n * ((bo[1] + bb) + n * ((bo[2] + c) + n * (size_t)(bo[3] + d)))];
+  }
+  qlb_basis_destroy(mini);
+  return rc;
+}
+
+// =================================================================== NCCL (loaded lazily; one process per GPU)
+namespace {
+typedef ncclResult_t (*fn_GetUniqueId)(ncclUniqueId *);
+typedef ncclResult_t (*fn_CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+typedef ncclResult_t (*fn_AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+typedef ncclResult_t (*fn_CommDestroy)(ncclComm_t);
+typedef const char *(*fn_GetErrorString)(ncclResult_t);
+fn_GetUniqueId p_GetUniqueId;
+fn_CommInitRank p_CommInitRank;
+fn_AllReduce p_AllReduce;
+fn_CommDestroy p_CommDestroy;
+fn_GetErrorString p_GetErrorString;
+
+int load_nccl() {
+  Engine &e = g_engine;
+  if (e.nccl_lib) return QLB_OK;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    e.nccl_lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (e.nccl_lib) break;
+  }
+  if (!e.nccl_lib) {
+    set_error(std::string("cannot dlopen libnccl: ") + dlerror());
+    return QLB_ERR_NCCL;
+  }
+  p_GetUniqueId = (fn_GetUniqueId)dlsym(e.nccl_lib, "ncclGetUniqueId");
+  p_CommInitRank = (fn_CommInitRank)dlsym(e.nccl_lib, "ncclCommInitRank");
+  p_AllReduce = (fn_AllReduce)dlsym(e.nccl_lib, "ncclAllReduce");
+  p_CommDestroy = (fn_CommDestroy)dlsym(e.nccl_lib, "ncclCommDestroy");
+  p_GetErrorString = (fn_GetErrorString)dlsym(e.nccl_lib, "ncclGetErrorString");
+  if (!p_GetUniqueId || !p_CommInitRank || !p_AllReduce || !p_CommDestroy) {
+    set_error("libnccl lacks a required symbol");
+    return QLB_ERR_NCCL;
+  }
+  return QLB_OK;
+}
+int nccl_fail(ncclResult_t r, const char *what) {
+  set_error(std::string("NCCL error in ") + what + ": " + (p_GetErrorString ? p_GetErrorString(r) : "?"));
+  return QLB_ERR_NCCL;
+}
+}  // namespace
+
+extern "C" int qlb_comm_unique_id(void *id128) {
+  if (!id128) return QLB_ERR_ARG;
+  if (int rc = load_nccl()) return rc;
+  ncclUniqueId id;
+  ncclResult_t r = p_GetUniqueId(&id);
+  if (r != ncclSuccess) return nccl_fail(r, "ncclGetUniqueId");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, 128);
+  return QLB_OK;
+}
+
+extern "C" int qlb_comm_init(const void *id128, int rank, int nranks) {
+  if (int rc = require_ready()) return rc;
+  if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return QLB_ERR_ARG;
+  if (int rc = load_nccl()) return rc;
+  Engine &e = g_engine;
+  QLB_CUDA(cudaSetDevice(e.device));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  ncclComm_t comm;
+  ncclResult_t r = p_CommInitRank(&comm, nranks, id, rank);
+  if (r != ncclSuccess) return nccl_fail(r, "ncclCommInitRank");
+  e.nccl_comm = (void *)comm;
+  e.rank = rank;
+  e.nranks = nranks;
+  return QLB_OK;
+}
+
+extern "C" int qlb_comm_destroy(void) {
+  Engine &e = g_engine;
+  if (e.nccl_comm && p_CommDestroy) p_CommDestroy((ncclComm_t)e.nccl_comm);
+  e.nccl_comm = nullptr;
+  e.rank = 0;
+  e.nranks = 1;
+  return QLB_OK;
+}
+
+extern "C" int qlb_allreduce_jk_device(qlb_basis *b, double *dJK, void *stream_) {
+  if (int rc = require_ready()) return rc;
+  Engine &e = g_engine;
+  if (!b || !dJK) return QLB_ERR_ARG;
+  if (!e.nccl_comm) {
+    set_error("qlb_allreduce_jk_device: no communicator (qlb_comm_init)");
+    return QLB_ERR_STATE;
+  }
+  cudaStream_t s = stream_ ? (cudaStream_t)stream_ : e.stream;
+  const size_t n = 2 * (size_t)b->nbf * b->nbf;
+  ncclResult_t r = p_AllReduce(dJK, dJK, n, ncclDouble, ncclSum, (ncclComm_t)e.nccl_comm, s);
+  if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce");
+  return QLB_OK;
+}
+
+// =================================================================== one-electron matrices
+static int one_electron_host(qlb_basis *b, int which, int natoms, const double *xyz, const double *Z, double *out) {
+  if (int rc = require_ready()) return rc;
+  if (!b || !out || (which == 2 && (natoms <= 0 || !xyz || !Z))) return QLB_ERR_ARG;
+  Engine &e = g_engine;
+  QLB_CUDA(cudaSetDevice(e.device));
+  const size_t N2 = (size_t)b->nbf * b->nbf;
+  double *d_at = nullptr;
+  if (which == 2) {
+    std::vector<double> at(4 * (size_t)natoms);
+    for (int i = 0; i < natoms; ++i) {
+      at[4 * i] = xyz[3 * i]; at[4 * i + 1] = xyz[3 * i + 1]; at[4 * i + 2] = xyz[3 * i + 2]; at[4 * i + 3] = Z[i];
+    }
+    QLB_CUDA(cudaMalloc((void **)&d_at, at.size() * sizeof(double)));
+    QLB_CUDA(cudaMemcpy(d_at, at.data(), at.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  int rc = one_electron_device(b, which, natoms, d_at, b->d_H, e.stream);
+  if (rc == QLB_OK) {
+    cudaError_t ce = cudaMemcpyAsync(out, b->d_H, N2 * sizeof(double), cudaMemcpyDeviceToHost, e.stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e.stream);
+    if (ce != cudaSuccess) rc = cuda_fail(ce, "one-electron D2H");
+  }
+  if (d_at) cudaFree(d_at);
+  return rc;
+}
+extern "C" int qlb_overlap(qlb_basis *b, double *S) { return one_electron_host(b, 0, 0, nullptr, nullptr, S); }
+extern "C" int qlb_kinetic(qlb_basis *b, double *T) { return one_electron_host(b, 1, 0, nullptr, nullptr, T); }
+extern "C" int qlb_nuclear_attraction(qlb_basis *b, int natoms, const double *xyz, const double *Z, double *V) {
+  return one_electron_host(b, 2, natoms, xyz, Z, V);
+}

@@ -1,0 +1,79 @@
+// qlb_internal.h -- host-side structures shared by the translation units of libqlb200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/qlb200.h"
+#include "eri_kernels.cuh"
+
+namespace qlb {
+
+constexpr int NCLASS = QLB_NCLASS;    // ss ps pp ds dp dd
+constexpr int NQCLASS = QLB_NQCLASS;  // X>=Y pairs of the above
+inline int class_of(int la, int lb) { return la * (la + 1) / 2 + lb; }
+inline void class_L(int c, int &la, int &lb) {
+  la = 0;
+  while ((la + 1) * (la + 2) / 2 <= c) ++la;
+  lb = c - la * (la + 1) / 2;
+}
+inline int qclass_of(int X, int Y) { return X * (X + 1) / 2 + Y; }
+
+struct Engine {
+  bool ready = false;
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  double *d_boys = nullptr;
+  bool profiling = false;
+  // NCCL (loaded lazily with dlopen)
+  void *nccl_lib = nullptr;
+  void *nccl_comm = nullptr;
+  int rank = 0, nranks = 1;
+};
+Engine &engine();
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+#define QLB_CUDA(call)                                   \
+  do {                                                   \
+    cudaError_t _e = (call);                             \
+    if (_e != cudaSuccess) return cuda_fail(_e, #call);  \
+  } while (0)
+
+}  // namespace qlb
+
+struct qlb_basis {
+  int nsh = 0, nbf = 0, nprim_total = 0;
+  std::vector<double> h_xyz, h_exps, h_coefs;
+  std::vector<int> h_L, h_nprim, h_poff, h_boff;
+  // pairs, sorted by class then Schwarz bound (descending)
+  int64_t npairs = 0;
+  std::vector<int> h_pair_a, h_pair_b, h_pair_poff, h_pair_ql;
+  std::vector<double> h_pair_Q;
+  int class_off[qlb::NCLASS + 1] = {0};
+  int qlmax = -32768;
+  // device
+  double *d_xyz = nullptr, *d_exps = nullptr, *d_coefs = nullptr;
+  int *d_poff = nullptr, *d_boff = nullptr, *d_L = nullptr;
+  int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pair_poff = nullptr, *d_pair_ql = nullptr;
+  double *d_pair_Q = nullptr;
+  double *d_pp[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // p, x, y, z, k
+  int64_t nprimpairs = 0;
+  // per-build scratch
+  double *d_P = nullptr, *d_JK = nullptr, *d_H = nullptr;  // N*N, 2*N*N, N*N
+  int *d_dl = nullptr;                                      // nsh*nsh (+1 slot for the max)
+  unsigned long long *d_counters = nullptr;                 // 2 per quartet class
+  cudaEvent_t ev[2 * qlb::NQCLASS + 4] = {nullptr};
+};
+
+namespace qlb {
+// class kernel launchers (class_kernels.cu)
+int launch_class_kernel(int X, int Y, int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_schwarz_kernel(int X, unsigned grid, cudaStream_t s, const SchwarzParams &prm);
+// flops per primitive quartet / digestion flops per contracted quartet for a quartet class
+void class_flops(int X, int Y, double &f_prim, double &f_digest);
+// one-electron kernels (one_electron.cu)
+int one_electron_device(qlb_basis *b, int which, int natoms, const double *d_xyzZ, double *d_out, cudaStream_t s);
+}  // namespace qlb

@@ -1,0 +1,52 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol the header declares,
+and refuses to compute without a device (no CPU fallback)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "qlb200.h")).read()
+    return sorted(set(re.findall(r"\b(qlb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from quantumlab_jl_b200 import libqlb
+
+    if not os.path.isfile(libqlb.LIB_PATH):
+        import __graft_entry__
+
+        __graft_entry__.build()
+    lib = libqlb.load()
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+    assert set(names) == set(libqlb.EXPORTS)
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from quantumlab_jl_b200 import libqlb
+    from quantumlab_jl_b200.b200shells import B200Shells
+    from quantumlab_jl_b200.base import LQuantumNumber, origin
+    from quantumlab_jl_b200.shell import Shell
+
+    with pytest.raises(libqlb.QlbError):
+        B200Shells([Shell(origin, LQuantumNumber("S"), [1.0], [1.0])])
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "quantumlab_jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                for pat in ("import oracle", "from oracle", "liboracle", "ql_oracle", "orc_"):
+                    assert pat not in src, (f, pat)

@@ -1,0 +1,228 @@
+"""GPU parity tests: libqlb200 (through its C ABI, via the host-side mirror of the reference API) against the CPU
+oracle on the same inputs.  Tolerances are the north star's: 1e-10 Eh per integral and per Fock element, 1e-8 Eh on
+the RHF energy; screening counts bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import atoms_of, make_basis
+
+pytestmark = pytest.mark.gpu
+
+TOL_INT = 1e-10
+
+
+@pytest.fixture(scope="module")
+def qlb():
+    from quantumlab_jl_b200 import libqlb
+
+    libqlb.init()
+    return libqlb
+
+
+def _b200(shells, **kw):
+    from quantumlab_jl_b200.b200shells import B200Shells
+
+    return B200Shells(shells, **kw)
+
+
+def _rand_sym(n, seed, scale=1.0):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((n, n)) * scale
+    return A + A.T
+
+
+def test_device_is_blackwell(qlb):
+    info = qlb.device_info()
+    assert info["cc"][0] >= 10 and info["sm_count"] > 0
+
+
+def test_eri_tensor_h2o_sto3g(orc, qlb):
+    geo, shells, b, _ = make_basis(orc, "h2o_sto3g")
+    ref = orc.eri_tensor(b, literal=True)
+    dev = _b200(shells)
+    got = dev.eri_tensor()
+    assert np.abs(got - ref).max() < 1e-12
+    # reference KAT runtests.jl:120 and the BASELINE.md golden
+    blk = dev.eri_block(0, 4, 3, 3)
+    assert abs(blk[0, 0, 1, 1] - got[0, 6, 4, 4]) < 1e-14
+    assert abs(blk[0, 0, 1, 1] - 0.1492228667247951) < 1e-12
+    # the literal reference (Gamma-difference Boys, clamp) agrees for s/p shells to its own accuracy
+    quirk = orc.eri_tensor(b, mode=orc.BOYS_REFQUIRK, literal=True)
+    assert np.abs(got - quirk).max() < 1e-9
+
+
+@pytest.mark.parametrize("name", ["h2o_631gs", "h2o_ccpvdz", "c2h6_def2svp"])
+def test_eri_blocks_all_classes(orc, qlb, name):
+    geo, shells, b, _ = make_basis(orc, name)
+    dev = _b200(shells)
+    rng = np.random.default_rng(3)
+    byL = {}
+    for i, s in enumerate(shells):
+        byL.setdefault(s.lqn.exponent, []).append(i)
+    Ls = sorted(byL)
+    quartets = []
+    for la in Ls:
+        for lb in Ls:
+            for lc in Ls:
+                for ld in Ls:
+                    quartets.append(tuple(int(rng.choice(byL[l])) for l in (la, lb, lc, ld)))
+    worst = 0.0
+    for (i, j, k, l) in quartets:
+        ref = orc.eri_block(b, i, j, k, l, literal=False)  # Cook closed form, exact Boys: the oracle of record
+        got = dev.eri_block(i, j, k, l)
+        assert got.shape == ref.shape
+        worst = max(worst, np.abs(got - ref).max())
+    assert worst < TOL_INT, worst
+
+
+def test_schwarz_bounds(orc, qlb):
+    geo, shells, b, _ = make_basis(orc, "h2o2_631gs")
+    dev = _b200(shells)
+    Q = dev.schwarz()
+    Qr = orc.schwarz(b)
+    assert np.abs(Q - Qr).max() < 1e-12 * max(1.0, Qr.max())
+    assert np.allclose(Q, Q.T)
+
+
+@pytest.mark.parametrize("name,tau", [("h2o_sto3g", 0.0), ("h2o_631gs", 0.0), ("h2o2_631gs", 1e-12), ("h2o4_631gs", 1e-10),
+                                      ("c2h6_def2svp", 1e-12), ("h2o_ccpvdz", 1e-12)])
+def test_jk_against_oracle(orc, qlb, name, tau):
+    geo, shells, b, _ = make_basis(orc, name)
+    dev = _b200(shells)
+    P = _rand_sym(b.N, 7, 0.3)
+    J, K = dev.build_jk(P, tau=tau)
+    Q = dev.schwarz()
+    Jr, Kr, counts = orc.md_jk(b, P, tau=tau if tau > 0 else 1e-300, Q=Q)
+    assert np.abs(J - Jr).max() < TOL_INT and np.abs(K - Kr).max() < TOL_INT
+    assert np.array_equal(J, J.T) and np.array_equal(K, K.T)
+    st = dev.last_stats
+    assert st["quartets_unique"] == counts[1]
+    assert st["quartets_kept"] == counts[0]  # bit-exact screening count (integer rule, device bounds)
+    F = dev.fock(np.zeros_like(P), P, tau=tau)
+    assert np.abs(F - (2 * Jr - Kr)).max() < 3 * TOL_INT
+
+
+def test_jk_equals_reference_full_loop(orc, qlb):
+    # the reference's own contraction: all nsh^4 ordered quartets, separate J and K passes
+    geo, shells, b, _ = make_basis(orc, "h2o_sto3g")
+    dev = _b200(shells)
+    P = _rand_sym(b.N, 11)
+    Jr, _ = orc.ref_contract(b, P, "J", literal=True)
+    Kr, _ = orc.ref_contract(b, P, "K", literal=True)
+    J, K = dev.build_jk(P, tau=0.0)
+    assert np.abs(J - Jr).max() < TOL_INT and np.abs(K - Kr).max() < TOL_INT
+
+
+def test_screening_counts_density_dependent(orc, qlb):
+    geo, shells, b, _ = make_basis(orc, "h2o4_631gs")
+    dev = _b200(shells)
+    Q = dev.schwarz()
+    rng = np.random.default_rng(5)
+    for scale, tau in ((1.0, 1e-8), (1e-3, 1e-9), (1e-6, 1e-10)):
+        A = rng.standard_normal((b.N, b.N)) * scale * np.exp(-3 * rng.random((b.N, b.N)) * 8)
+        P = A + A.T
+        dev.build_jk(P, tau=tau)
+        kept, vis = orc.screen_count(b, Q, P, tau)
+        assert dev.last_stats["quartets_kept"] == kept and dev.last_stats["quartets_unique"] == vis
+        assert 0 < kept < vis
+
+
+def test_jk_linearity_and_zero(orc, qlb):
+    geo, shells, b, _ = make_basis(orc, "h2o2_631gs")
+    dev = _b200(shells)
+    P1, P2 = _rand_sym(b.N, 1), _rand_sym(b.N, 2)
+    J1, K1 = dev.build_jk(P1, tau=0.0)
+    J2, K2 = dev.build_jk(P2, tau=0.0)
+    J3, K3 = dev.build_jk(P1 + 2 * P2, tau=0.0)
+    assert np.abs(J3 - (J1 + 2 * J2)).max() < 1e-9 and np.abs(K3 - (K1 + 2 * K2)).max() < 1e-9
+    J0, K0 = dev.build_jk(np.zeros((b.N, b.N)))
+    assert not J0.any() and not K0.any()
+    assert dev.last_stats["quartets_kept"] == 0
+
+
+def test_one_electron_matrices(orc, qlb):
+    for name in ("h2o_sto3g", "h2o_631gs", "c2h6_def2svp"):
+        geo, shells, b, _ = make_basis(orc, name)
+        xyz, Z = atoms_of(geo)
+        dev = _b200(shells)
+        assert np.abs(dev.one_electron("overlap") - orc.one_electron(b, "overlap")).max() < 1e-12
+        assert np.abs(dev.one_electron("kinetic") - orc.one_electron(b, "kinetic")).max() < 1e-11
+        assert np.abs(dev.one_electron("nuclear", geo) - orc.one_electron(b, "nuclear", xyz, Z)).max() < 1e-10
+
+
+def test_scf_h2o_sto3g_reference_kat(orc, qlb):
+    # runtests.jl:84: total RHF energy -74.96178985 (1e-7); BASELINE.md: 11 Roothaan iterations from ZeroGuess
+    from quantumlab_jl_b200.geometry import computeEnergyInteratomicRepulsion
+    from quantumlab_jl_b200.hartreefock import evaluateSCF
+    from quantumlab_jl_b200.initialguess import ZeroGuess
+
+    geo, shells, b, nocc = make_basis(orc, "h2o_sto3g")
+    eps, E, P = evaluateSCF(_b200(shells), geo, ZeroGuess, nocc, info=False)
+    assert evaluateSCF.last_iterations == 11
+    assert abs(E + computeEnergyInteratomicRepulsion(geo) - (-74.96178985)) < 1e-7
+    assert abs(E - (-84.2254524222)) < 1e-8
+    # same through the Ionization default and a plain Shell list
+    eps2, E2, P2 = evaluateSCF(shells, geo, ZeroGuess, info=False)
+    assert abs(E2 - E) < 1e-12
+
+
+def test_fock_sad_kat(orc, qlb):
+    # runtests.jl:148 mean(computeMatrixFock(bas,h2o,SAD alpha)) = -0.785008186026 (1e-7)
+    from quantumlab_jl_b200.initialguess import SAD_STO3G_ALPHA, sad_density
+    from quantumlab_jl_b200.specialmatrices import computeMatrixFock
+
+    geo, shells, b, _ = make_basis(orc, "h2o_sto3g")
+    F = computeMatrixFock(shells, geo, sad_density(geo, SAD_STO3G_ALPHA))
+    assert abs(F.mean() - (-0.785008186026)) < 1e-7
+
+
+def test_scf_energy_dshell_vs_oracle(orc, qlb):
+    # d shells: oracle of record = closed form with exact Boys; SCF energy to 1e-8 Eh
+    from quantumlab_jl_b200.hartreefock import evaluateSCF
+    from quantumlab_jl_b200.initialguess import ZeroGuess
+
+    geo, shells, b, nocc = make_basis(orc, "h2o_631gs")
+    xyz, Z = atoms_of(geo)
+    S, T = orc.one_electron(b, "overlap"), orc.one_electron(b, "kinetic")
+    V = orc.one_electron(b, "nuclear", xyz, Z)
+    Q = orc.schwarz(b)
+    jk = {}
+
+    def oj(P):
+        key = P.tobytes()
+        if key not in jk:
+            jk.clear()
+            jk[key] = orc.md_jk(b, P, tau=1e-14, Q=Q)
+        return jk[key]
+
+    _, Er, Pr, itr = orc.evaluate_scf(np.zeros((b.N, b.N)), S, T, V, lambda P: oj(P)[0], lambda P: oj(P)[1], nocc)
+    eps, E, P = evaluateSCF(_b200(shells), geo, ZeroGuess, nocc, info=False)
+    assert abs(E - Er) < 1e-8
+    assert evaluateSCF.last_iterations == itr
+
+
+def test_benzene_ccpvdz_full_build(orc, qlb):
+    geo, shells, b, nocc = make_basis(orc, "benzene_ccpvdz")
+    assert b.N == 120 and b.nsh == 54
+    dev = _b200(shells)
+    P = _rand_sym(b.N, 13, 0.2)
+    J, K = dev.build_jk(P, tau=1e-12)
+    Jr, Kr, counts = orc.md_jk(b, P, tau=1e-12, Q=dev.schwarz())
+    assert dev.last_stats["quartets_kept"] == counts[0]
+    assert np.abs(J - Jr).max() < TOL_INT and np.abs(K - Kr).max() < TOL_INT
+
+
+def test_bad_arguments_raise(qlb):
+    from quantumlab_jl_b200.base import LQuantumNumber, origin
+    from quantumlab_jl_b200.shell import Shell
+
+    with pytest.raises(qlb.QlbError):
+        _b200([Shell(origin, LQuantumNumber("F"), [1.0], [1.0])])  # L > QLB_MAX_L, cf. LibInt2Module.jl:79-83
+    dev = _b200([Shell(origin, LQuantumNumber("S"), [1.0], [1.0])])
+    with pytest.raises(ValueError):
+        dev.build_jk(np.zeros((3, 3)))
+    with pytest.raises(qlb.QlbError):
+        dev.eri_block(0, 0, 0, 5)
+    dev.destroy()
+    with pytest.raises(qlb.QlbError):
+        dev.build_jk(np.zeros((1, 1)))
