@@ -106,6 +106,8 @@ class B200Shells(list):
     def eri_block(self, i: int, j: int, k: int, l: int) -> np.ndarray:
         from .shell import nbf
 
+        if not all(0 <= s < len(self) for s in (i, j, k, l)):
+            raise libqlb.QlbError(f"shell index out of range 0..{len(self) - 1}: {(i, j, k, l)}")
         shp = tuple(nbf(self[s]) for s in (i, j, k, l))
         out = np.empty(shp, dtype=np.float64, order="F")
         libqlb.check(libqlb.load().qlb_eri_block(self.handle, i, j, k, l, libqlb.dptr(out)))

@@ -48,7 +48,7 @@ def test_eri_tensor_h2o_sto3g(orc, qlb):
     assert abs(blk[0, 0, 1, 1] - 0.1492228667247951) < 1e-12
     # the literal reference (Gamma-difference Boys, clamp) agrees for s/p shells to its own accuracy
     quirk = orc.eri_tensor(b, mode=orc.BOYS_REFQUIRK, literal=True)
-    assert np.abs(got - quirk).max() < 1e-9
+    assert np.abs(got - quirk).max() < 1e-8  # the Gamma-difference Boys routine is only ~1e-9 accurate here
 
 
 @pytest.mark.parametrize("name", ["h2o_631gs", "h2o_ccpvdz", "c2h6_def2svp"])
