@@ -122,6 +122,17 @@ def ref_contract(b: Basis, P, which: str, mode=BOYS_EXACT, literal=True, stride=
     return out.reshape((b.N, b.N), order="F"), nq.value
 
 
+def ref_contract_sampled(b: Basis, P, which: str, stride: int, offset: int = 0, nthreads: int = 1, mode=BOYS_REFQUIRK, literal=True):
+    """Uniform sample (every stride-th quartet) of the reference's nsh^4 direct contraction; -> (partial matrix, nquartets)."""
+    Pf = np.asfortranarray(P, dtype=np.float64)
+    out = np.zeros(b.N * b.N, dtype=np.float64)
+    f = lib().orc_ref_contract_sampled
+    f.restype = C.c_long
+    n = f(*b.args(), _p(Pf.reshape(-1, order="F")), C.c_int(0 if which == "J" else 1), C.c_int(mode), C.c_int(int(literal)),
+          C.c_long(stride), C.c_long(offset), C.c_int(nthreads), _p(out))
+    return out.reshape((b.N, b.N), order="F"), int(n)
+
+
 def schwarz(b: Basis):
     Q = np.zeros(b.nsh * b.nsh, dtype=np.float64)
     lib().orc_md_schwarz(*b.args(), _p(Q))

@@ -424,6 +424,64 @@ void orc_ref_contract(int nsh, const double *centers, const int *L, const int *n
   basis_free(&b);
 }
 
+/* Sampled, optionally multi-threaded timing form of the reference's direct contraction
+ * (SpecialMatricesModule.jl:33-100): evaluates every `stride`-th quartet of the ordered nsh^4 loop (uniform sample),
+ * for J (which=0) or K (which=1), with `nthreads` OpenMP threads (the reference itself is single-threaded; >1 models
+ * the reference algorithm spread over all host cores).  Returns the number of shell quartets evaluated; `out` gets
+ * the (partial) contraction so the work cannot be optimised away. */
+long orc_ref_contract_sampled(int nsh, const double *centers, const int *L, const int *nprim, const double *exps,
+                              const double *coefs, const double *P, int which, int boys_mode, int literal, long stride,
+                              long offset, int nthreads, double *out) {
+  basis_t b; basis_init(&b, nsh, centers, L, nprim, exps, coefs);
+  long N = b.boff[nsh];
+  memset(out, 0, sizeof(double) * N * N);
+  long total = (long)nsh * nsh * nsh * nsh;
+  long nsample = (total - offset + stride - 1) / stride;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+  {
+    double *loc = (double *)calloc(N * N, sizeof(double));
+    double blk[1296];
+#pragma omp for schedule(dynamic, 16)
+    for (long s = 0; s < nsample; s++) {
+      long q = offset + s * stride;
+      int s4 = (int)(q % nsh); q /= nsh;
+      int s3 = (int)(q % nsh); q /= nsh;
+      int s2 = (int)(q % nsh); q /= nsh;
+      int s1 = (int)q;
+      int n1 = NCART(L[s1]), n2 = NCART(L[s2]), n3 = NCART(L[s3]), n4 = NCART(L[s4]);
+      if (which == 0) {
+        cook_block(&b, s1, s2, s3, s4, boys_mode, literal, blk);
+        for (int mu = 0; mu < n1; mu++)
+          for (int nu = 0; nu < n2; nu++) {
+            double acc = 0.0;
+            for (int si = 0; si < n4; si++)
+              for (int la = 0; la < n3; la++)
+                acc += blk[mu + n1 * (nu + n2 * (la + n3 * si))] * P[(b.boff[s3] + la) + N * (b.boff[s4] + si)];
+            loc[(b.boff[s1] + mu) + N * (b.boff[s2] + nu)] += acc;
+          }
+      } else {
+        cook_block(&b, s1, s3, s2, s4, boys_mode, literal, blk);
+        for (int mu = 0; mu < n1; mu++)
+          for (int nu = 0; nu < n2; nu++) {
+            double acc = 0.0;
+            for (int si = 0; si < n4; si++)
+              for (int la = 0; la < n3; la++)
+                acc += blk[mu + n1 * (la + n3 * (nu + n2 * si))] * P[(b.boff[s3] + la) + N * (b.boff[s4] + si)];
+            loc[(b.boff[s1] + mu) + N * (b.boff[s2] + nu)] += acc;
+          }
+      }
+    }
+#pragma omp critical
+    for (long t = 0; t < N * N; t++) out[t] += loc[t];
+    free(loc);
+  }
+  basis_free(&b);
+  return nsample;
+}
+
 /* ------------------------------------------------------------------ one-electron integrals (for the KATs) */
 /* IntegralsModule.jl:39-49 GaussianIntegral1D_Mathematica */
 static double gint1d(int m, double z) {

@@ -1,54 +1,54 @@
-// class_kernels.cu -- instantiation + launch table of the 21 canonical (ab|cd) class kernels (s,p,d).
+// class_kernels.cu -- launch table of the 21 canonical (ab|cd) class kernels (s,p,d) + Schwarz kernels + flop model.
 #include "qlb_internal.h"
 
 namespace qlb {
 
-// UNR / DSTEP policy per class lives here (see DESIGN.md "Kernel K4").
-template <int LA, int LB, int LC, int LD>
-struct Policy {
-  static constexpr int L = LA + LB + LC + LD;
-  static constexpr bool unroll = (L <= 2);                 // fully unrolled, register resident
-  static constexpr int dstep = ncart(LD);                   // single pass over the ket-d components
-};
-
-template <int LA, int LB, int LC, int LD>
-static int launch4(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm) {
-  using Pol = Policy<LA, LB, LC, LD>;
-  const dim3 block(TILE_KET, TILE_BRA);
-  if (mode == 0)
-    eri_class_kernel<LA, LB, LC, LD, Pol::unroll, 0, Pol::dstep><<<grid, block, 0, s>>>(prm);
-  else
-    eri_class_kernel<LA, LB, LC, LD, false, 1, ncart(LD)><<<grid, block, 0, s>>>(prm);
-  return (int)cudaGetLastError();
-}
-
-#define QLB_CASE(X, Y, LA, LB, LC, LD) \
-  case (X) * ((X) + 1) / 2 + (Y):      \
-    return launch4<LA, LB, LC, LD>(mode, grid, s, prm);
+// one launcher per class, each defined in its own translation unit (class_tu.cu compiled with -DQC_*)
+int launch_qc_0000(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_1000(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_1010(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_1100(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_1110(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_1111(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_2000(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_2010(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_2011(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_2020(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_2100(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_2110(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_2111(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_2120(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_2121(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_2200(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_2210(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_2211(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_2220(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_2221(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_2222(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
 
 int launch_class_kernel(int X, int Y, int mode, unsigned grid, cudaStream_t s, const ClassParams &prm) {
   switch (qclass_of(X, Y)) {
-    QLB_CASE(0, 0, 0, 0, 0, 0)
-    QLB_CASE(1, 0, 1, 0, 0, 0)
-    QLB_CASE(1, 1, 1, 0, 1, 0)
-    QLB_CASE(2, 0, 1, 1, 0, 0)
-    QLB_CASE(2, 1, 1, 1, 1, 0)
-    QLB_CASE(2, 2, 1, 1, 1, 1)
-    QLB_CASE(3, 0, 2, 0, 0, 0)
-    QLB_CASE(3, 1, 2, 0, 1, 0)
-    QLB_CASE(3, 2, 2, 0, 1, 1)
-    QLB_CASE(3, 3, 2, 0, 2, 0)
-    QLB_CASE(4, 0, 2, 1, 0, 0)
-    QLB_CASE(4, 1, 2, 1, 1, 0)
-    QLB_CASE(4, 2, 2, 1, 1, 1)
-    QLB_CASE(4, 3, 2, 1, 2, 0)
-    QLB_CASE(4, 4, 2, 1, 2, 1)
-    QLB_CASE(5, 0, 2, 2, 0, 0)
-    QLB_CASE(5, 1, 2, 2, 1, 0)
-    QLB_CASE(5, 2, 2, 2, 1, 1)
-    QLB_CASE(5, 3, 2, 2, 2, 0)
-    QLB_CASE(5, 4, 2, 2, 2, 1)
-    QLB_CASE(5, 5, 2, 2, 2, 2)
+    case 0: return launch_qc_0000(mode, grid, s, prm);  // (ss|ss)
+    case 1: return launch_qc_1000(mode, grid, s, prm);  // (ps|ss)
+    case 2: return launch_qc_1010(mode, grid, s, prm);  // (ps|ps)
+    case 3: return launch_qc_1100(mode, grid, s, prm);  // (pp|ss)
+    case 4: return launch_qc_1110(mode, grid, s, prm);  // (pp|ps)
+    case 5: return launch_qc_1111(mode, grid, s, prm);  // (pp|pp)
+    case 6: return launch_qc_2000(mode, grid, s, prm);  // (ds|ss)
+    case 7: return launch_qc_2010(mode, grid, s, prm);  // (ds|ps)
+    case 8: return launch_qc_2011(mode, grid, s, prm);  // (ds|pp)
+    case 9: return launch_qc_2020(mode, grid, s, prm);  // (ds|ds)
+    case 10: return launch_qc_2100(mode, grid, s, prm);  // (dp|ss)
+    case 11: return launch_qc_2110(mode, grid, s, prm);  // (dp|ps)
+    case 12: return launch_qc_2111(mode, grid, s, prm);  // (dp|pp)
+    case 13: return launch_qc_2120(mode, grid, s, prm);  // (dp|ds)
+    case 14: return launch_qc_2121(mode, grid, s, prm);  // (dp|dp)
+    case 15: return launch_qc_2200(mode, grid, s, prm);  // (dd|ss)
+    case 16: return launch_qc_2210(mode, grid, s, prm);  // (dd|ps)
+    case 17: return launch_qc_2211(mode, grid, s, prm);  // (dd|pp)
+    case 18: return launch_qc_2220(mode, grid, s, prm);  // (dd|ds)
+    case 19: return launch_qc_2221(mode, grid, s, prm);  // (dd|dp)
+    case 20: return launch_qc_2222(mode, grid, s, prm);  // (dd|dd)
   }
   return (int)cudaErrorInvalidValue;
 }
