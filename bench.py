@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- Fock builds/s on the synthetic (H2O)_32 / 6-31G* water cluster (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--tau T]
+
+A "step" is ONE Fock build F = H + 2J - K for a fixed density P: screened, symmetry-unique shell quartets ->
+class-specialised FP64 ERI kernels with on-the-fly J/K digestion -> (N>1: one NCCL all-reduce of [J;K]) -> symmetrise
+-> F.  The quartet tiles of one build are sharded over the ranks (strong scaling: total work fixed).
+
+  value   device-resident: P, H already in HBM, F left in HBM; timed with CUDA events on the launching stream,
+          L2 flushed between steps, max over ranks.
+  e2e     the same build through the host-buffer C-ABI call a Julia caller makes (qlb_fock): pinned host P and H in,
+          F out, copies inside the timed region.
+  --impl reference   the reference ALGORITHM on the host cores (CPU oracle port: Cook closed form, per-term Boys via
+          the Gamma-difference formula, all nsh^4 ordered quartets, separate J and K passes, no screening), timed on a
+          bounded uniform sample of the quartet loop and extrapolated; Julia itself is not installed.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "fock_builds_per_s"
+UNIT = "builds/s"
+WORKLOAD_DESC = {
+    "h2o32_631gs": "(H2O)_32 water cluster, 6-31G*, RHF Fock build (N=608, 320 shells), density of SCF iteration 2",
+    "benzene_ccpvdz": "benzene cc-pVDZ RHF Fock build (N=120)",
+    "h2o64_ccpvdz": "(H2O)_64 cc-pVDZ RHF conventional Fock build (N=1600)",
+    "c40h82_def2svp": "C40H82 def2-SVP RHF Fock build (N=1010)",
+    "h2o4_631gs": "(H2O)_4 6-31G* (smoke size)",
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="h2o32_631gs")
+    ap.add_argument("--tau", type=float, default=1e-12)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU time budget of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def build_workload(name):
+    from quantumlab_jl_b200 import workloads
+
+    return workloads.build(name)
+
+
+def oracle_basis(shells):
+    from oracle import oracle as orc
+    from quantumlab_jl_b200.shell import flattenShells
+
+    orc.build()
+    return orc, orc.Basis(*flattenShells(shells))
+
+
+# ----------------------------------------------------------------------------------------------- CPU baselines
+def cpu_reference_sample(shells, P, budget_s, nthreads):
+    """Reference algorithm (SpecialMatricesModule.jl:33-100 over IntegralsModule.jl:412-462) on a uniform sample of the
+    nsh^4 ordered quartet loop; returns (builds/s extrapolated, description, seconds spent)."""
+    orc, b = oracle_basis(shells)
+    total = b.nsh ** 4
+    # calibrate on a small sample, then size the real one to the budget
+    n0 = 400 * max(1, nthreads)
+    t = time.perf_counter()
+    orc.ref_contract_sampled(b, P, "J", max(1, total // n0), 0, nthreads)
+    per_q = (time.perf_counter() - t) / min(n0, total)
+    n = int(min(total, max(n0, 0.5 * budget_s / max(per_q, 1e-9))))
+    stride = max(1, total // n)
+    spent = 0.0
+    nq = 0
+    for which, off in (("J", 0), ("K", stride // 2)):
+        t = time.perf_counter()
+        _, k = orc.ref_contract_sampled(b, P, which, stride, off % stride, nthreads)
+        spent += time.perf_counter() - t
+        nq += k
+    full_s = spent / nq * (2 * total)  # J pass + K pass over all nsh^4 ordered quartets
+    exact = stride == 1
+    desc = (f"{nq} of {2 * total} ordered shell quartets (uniform stride {stride}, J and K passes), "
+            f"{'full run' if exact else 'extrapolated'}; Cook closed form with the reference's Gamma-difference Boys")
+    return 1.0 / full_s, desc, spent
+
+
+def cpu_fair_sample(shells, P, tau, budget_s):
+    """Same algorithm family as the GPU path (MD, 8-fold symmetry, same screening), OpenMP over all host cores."""
+    orc, b = oracle_basis(shells)
+    Q = orc.schwarz(b)
+    npair = b.nsh * (b.nsh + 1) // 2
+    nranks = max(1, npair // 400)
+    t = time.perf_counter()
+    orc.md_jk(b, P, tau=tau, Q=Q, rank=0, nranks=nranks)
+    dt = time.perf_counter() - t
+    if dt < budget_s / 4 and nranks > 1:
+        nranks = max(1, int(nranks * dt / (budget_s / 2)))
+        t = time.perf_counter()
+        orc.md_jk(b, P, tau=tau, Q=Q, rank=0, nranks=nranks)
+        dt = time.perf_counter() - t
+    return 1.0 / (dt * nranks), f"1/{nranks} of the bra shell pairs (round-robin), extrapolated", orc.num_threads()
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    geo, shells, nocc = build_workload(args.workload)
+    orc, b = oracle_basis(shells)
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((b.N, b.N)) * 0.05
+    P = A + A.T  # the reference algorithm does not screen: its cost is independent of P
+    nthreads = os.cpu_count() or 1
+    vals, descs = [], None
+    for i in range(args.warmup + args.steps):
+        v, desc, _ = cpu_reference_sample(shells, P, max(2.0, args.cpu_seconds / max(1, args.steps)), nthreads)
+        if i >= args.warmup:
+            vals.append(v)
+            descs = desc
+    value = statistics.mean(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "name": args.workload, "nsh": b.nsh, "nbf": b.N},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": descs},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference algorithm restated in C (oracle/), OpenMP over the sampled quartets; Julia is not installed here",
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from quantumlab_jl_b200 import libqlb
+    from quantumlab_jl_b200.b200shells import B200Shells
+    from quantumlab_jl_b200.hartreefock import evaluateSCFStep
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = libqlb.init(local)
+    if world > 1:
+        idbuf = C.create_string_buffer(128)
+        if rank == 0:
+            libqlb.check(lib.qlb_comm_unique_id(idbuf))
+        obj = [idbuf.raw]
+        dist.broadcast_object_list(obj, src=0)
+        libqlb.check(lib.qlb_comm_init(C.create_string_buffer(obj[0], 128), rank, world))
+
+    geo, shells, nocc = build_workload(args.workload)
+    dev = B200Shells(shells, tau=args.tau)
+    N = dev.nbf
+    # ---- setup (untimed): one-electron matrices on the device, density of SCF iteration 2 from the zero guess
+    S = dev.one_electron("overlap")
+    T = dev.one_electron("kinetic")
+    V = dev.one_electron("nuclear", geo)
+    H = np.asfortranarray(T + V)
+    _, P = evaluateSCFStep(H, S, nocc)
+    F = dev.fock(H, P)
+    _, P = evaluateSCFStep(F, S, nocc)
+    P = np.asfortranarray(P)
+
+    # a dedicated (non-default) torch stream: its handle is what the C ABI launches on, and torch.cuda.Event records on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    sptr = C.c_void_p(stream.cuda_stream)
+    dP = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()  # column-major N x N == row-major transpose (P symmetric)
+    dH = torch.from_numpy(np.ascontiguousarray(H.T)).cuda()
+    dJK = torch.empty(2 * N * N, dtype=torch.float64, device="cuda")
+    dF = torch.empty(N * N, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # 256 MB > 126 MB L2
+    h = dev.handle
+    pJ, pK = C.c_void_p(dJK.data_ptr()), C.c_void_p(dJK.data_ptr() + 8 * N * N)
+
+    def step_device(stats=None):
+        libqlb.check(lib.qlb_build_jk_device(h, C.c_void_p(dP.data_ptr()), args.tau, pJ, pK, rank, world, sptr, stats))
+        if world > 1:
+            libqlb.check(lib.qlb_allreduce_jk_device(h, C.c_void_p(dJK.data_ptr()), sptr))
+        libqlb.check(lib.qlb_symmetrize_device(h, pJ, pK, sptr))
+        libqlb.check(lib.qlb_fock_device(h, C.c_void_p(dH.data_ptr()), pJ, pK, C.c_void_p(dF.data_ptr()), sptr))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # statistics of one build (untimed): quartet counts, launches, algorithmic flops, per-class times
+    lib.qlb_set_profiling(1)
+    st = libqlb.Stats()
+    step_device(C.byref(st))
+    torch.cuda.synchronize()
+    lib.qlb_set_profiling(0)
+    stats = st.as_dict()
+    launches_per_step = stats["kernel_launches"] + 3  # + 2 symmetrise + 1 Fock assembly
+    counts = torch.tensor([stats["quartets_kept"], sum(stats["prim_quartets_class"].values())], dtype=torch.float64, device="cuda")
+    flops = torch.tensor([stats["flops_algorithmic"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(counts)
+        dist.all_reduce(flops)
+    F_dev = dF.cpu().numpy().reshape(N, N)
+    check_err = float(np.abs(F_dev - F_dev.T).max())
+
+    # ---- timed region 1: device resident
+    for _ in range(args.warmup):
+        flush.zero_()
+        step_device()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b_ in ev:
+        flush.zero_()  # L2 flush between steps (outside the step's event pair)
+        a.record(stream)
+        step_device()
+        b_.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b_) for a, b_ in ev]
+    ms_local = sum(step_ms)
+    if rank == 0:
+        print("per-step ms:", " ".join(f"{x:.2f}" for x in step_ms), file=sys.stderr)
+    tms = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tms.item()) / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---- timed region 2: end to end through the host-buffer C-ABI call (pinned host buffers, copies inside)
+    hP = torch.from_numpy(P.copy(order="F").reshape(-1, order="F")).pin_memory()
+    hH = torch.from_numpy(H.copy(order="F").reshape(-1, order="F")).pin_memory()
+    hF = torch.empty(N * N, dtype=torch.float64).pin_memory()
+    dp_ = C.POINTER(C.c_double)
+
+    def step_e2e():
+        libqlb.check(lib.qlb_fock(h, C.cast(hH.data_ptr(), dp_), C.cast(hP.data_ptr(), dp_), args.tau, C.cast(hF.data_ptr(), dp_), None))
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step_e2e()
+    barrier()
+    t_e2e = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        step_e2e()  # synchronous: returns after F is in host memory
+        t_e2e += time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = args.steps / float(te.item())
+    e2e_err = float(np.abs(hF.numpy().reshape(N, N, order="F") - F_dev.T).max())
+
+    if rank == 0:
+        fp64_peak = libqlb.fp64_peak_probe()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        tot_flops = float(flops.item())
+        eri_ms = stats["ms_eri"]
+        per_class = {}
+        for k, ms in stats["ms_class"].items():
+            per_class[k] = {"ms": round(ms, 4), "quartets": stats["quartets_kept_class"].get(k, 0),
+                            "prim_quartets": stats["prim_quartets_class"].get(k, 0)}
+        achieved = stats["flops_algorithmic"] / (eri_ms * 1e-3) * 1e-12 if eri_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "name": args.workload, "nsh": len(shells),
+                       "nbf": N, "tau": args.tau, "parallelism": f"quartet tiles sharded over {world} rank(s), 1 NCCL all-reduce of [J;K]",
+                       "l2": "flushed between steps (256 MB write)", "timing": "per-step CUDA events on the launching stream, max over ranks"},
+            "quartets_per_s": float(counts[0].item()) * value,
+            "quartets_kept": int(counts[0].item()), "quartets_unique": stats["quartets_unique"],
+            "prim_quartets": int(counts[1].item()),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * N * N * 8, "d2h_bytes_per_step": N * N * 8,
+                    "max_abs_diff_vs_device_path": e2e_err},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "kernel": "eri_class_kernel<la,lb,lc,ld> (all 21 class instantiations of rank 0, CUDA-event time of the ERI section)",
+                         "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                         "algorithmic_flops_per_build": tot_flops, "hbm_gbs_measured": peaks.get("hbm_gbs"),
+                         "per_class": per_class},
+            "fock_symmetry_residual": check_err,
+        }
+        # CPU baselines on this box's host cores (bounded samples)
+        try:
+            if args.cpu_seconds <= 0:
+                raise RuntimeError("skipped (--cpu-seconds 0)")
+            v, desc, _ = cpu_reference_sample(shells, P, args.cpu_seconds, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
+            vf, descf, thr = cpu_fair_sample(shells, P, args.tau, args.cpu_seconds)
+            line["cpu_baseline_fair"] = {"value": vf, "unit": UNIT, "cores": thr, "kind": "port",
+                                         "sample": descf + "; McMurchie-Davidson, 8-fold symmetry, same screening, OpenMP"}
+        except Exception as exc:  # the oracle is test infrastructure: its absence must not hide the GPU number
+            line["cpu_baseline"] = {"error": repr(exc)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        lib.qlb_comm_destroy()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,7 +27,7 @@ static void make_boys_table(std::vector<double> &tab) {
   tab.assign((size_t)BOYS_NROW * BOYS_NCOL, 0.0);
   for (int i = 0; i < BOYS_NROW; ++i) {
     const long double T = (long double)i * (long double)BOYS_DT;
-    const int mtop = BOYS_NCOL - 1;
+    const int mtop = BOYS_NCOL - 2;
     // F_mtop(T) = exp(-T) sum_k (2T)^k / ((2m+1)(2m+3)...(2m+2k+1)), then downward recursion
     long double term = 1.0L / (2 * mtop + 1), sum = term;
     for (int k = 1; k < 2000; ++k) {
@@ -42,6 +42,7 @@ static void make_boys_table(std::vector<double> &tab) {
       F = (2.0L * T * F + ex) / (2 * m - 1);
       tab[(size_t)i * BOYS_NCOL + m - 1] = (double)F;
     }
+    tab[(size_t)i * BOYS_NCOL + BOYS_EXPCOL] = (double)ex;
   }
 }
 
@@ -50,8 +51,7 @@ static void make_boys_table(std::vector<double> &tab) {
 __global__ void pair_prim_kernel(int npairs, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
                                  const int *__restrict__ pair_poff, const double *__restrict__ xyz,
                                  const int *__restrict__ poff, const double *__restrict__ exps,
-                                 const double *__restrict__ coefs, double *pp_p, double *pp_x, double *pp_y, double *pp_z,
-                                 double *pp_k) {
+                                 const double *__restrict__ coefs, double2 *rec) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= npairs) return;
   const int a = pair_a[w], b = pair_b[w];
@@ -64,11 +64,10 @@ __global__ void pair_prim_kernel(int npairs, const int *__restrict__ pair_a, con
     const int ia = t / nb, ib = t - ia * nb;
     const double al = exps[oa + ia], be = exps[ob + ib];
     const double p = al + be, ip = 1.0 / p;
-    pp_p[base + t] = p;
-    pp_x[base + t] = (al * Ax + be * Bx) * ip;
-    pp_y[base + t] = (al * Ay + be * By) * ip;
-    pp_z[base + t] = (al * Az + be * Bz) * ip;
-    pp_k[base + t] = coefs[oa + ia] * coefs[ob + ib] * exp(-al * be * ip * ab2);
+    double2 *r = rec + 3 * (size_t)(base + t);
+    r[0] = make_double2(p, (al * Ax + be * Bx) * ip);
+    r[1] = make_double2((al * Ay + be * By) * ip, (al * Az + be * Bz) * ip);
+    r[2] = make_double2(coefs[oa + ia] * coefs[ob + ib] * exp(-al * be * ip * ab2) * ip, 0.5 * ip);
   }
 }
 
@@ -130,7 +129,7 @@ static int upload(T **dptr, const std::vector<T> &h) {
 }
 
 static void fill_pp(const qlb_basis *b, PrimPairs &pp) {
-  pp.p = b->d_pp[0]; pp.x = b->d_pp[1]; pp.y = b->d_pp[2]; pp.z = b->d_pp[3]; pp.k = b->d_pp[4];
+  pp.rec = b->d_pp;
 }
 
 static int run_pair_prims(qlb_basis *b) {
@@ -139,8 +138,7 @@ static int run_pair_prims(qlb_basis *b) {
   if (np == 0) return QLB_OK;
   const int threads = 256, blocks = (int)(((int64_t)np * 32 + threads - 1) / threads);
   pair_prim_kernel<<<blocks, threads, 0, e.stream>>>(np, b->d_pair_a, b->d_pair_b, b->d_pair_poff, b->d_xyz, b->d_poff,
-                                                     b->d_exps, b->d_coefs, b->d_pp[0], b->d_pp[1], b->d_pp[2], b->d_pp[3],
-                                                     b->d_pp[4]);
+                                                     b->d_exps, b->d_coefs, b->d_pp);
   QLB_CUDA(cudaGetLastError());
   return QLB_OK;
 }
@@ -262,7 +260,7 @@ extern "C" int qlb_basis_destroy(qlb_basis *b) {
   if (!b) return QLB_OK;
   if (g_engine.ready) cudaSetDevice(g_engine.device);
   void *ptrs[] = {b->d_xyz, b->d_exps, b->d_coefs, b->d_poff, b->d_boff, b->d_L, b->d_pair_a, b->d_pair_b,
-                  b->d_pair_poff, b->d_pair_ql, b->d_pair_Q, b->d_pp[0], b->d_pp[1], b->d_pp[2], b->d_pp[3], b->d_pp[4],
+                  b->d_pair_poff, b->d_pair_ql, b->d_pair_Q, b->d_pp,
                   b->d_P, b->d_JK, b->d_H, b->d_dl, b->d_counters};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -302,7 +300,7 @@ static int basis_build_pairs(qlb_basis *b) {
   if (int rc = upload(&b->d_pair_a, b->h_pair_a)) return rc;
   if (int rc = upload(&b->d_pair_b, b->h_pair_b)) return rc;
   if (int rc = upload(&b->d_pair_poff, b->h_pair_poff)) return rc;
-  for (int k = 0; k < 5; ++k) QLB_CUDA(cudaMalloc((void **)&b->d_pp[k], std::max<int64_t>(b->nprimpairs, 1) * sizeof(double)));
+  QLB_CUDA(cudaMalloc((void **)&b->d_pp, std::max<int64_t>(b->nprimpairs, 1) * 3 * sizeof(double2)));
   QLB_CUDA(cudaMalloc((void **)&b->d_pair_Q, std::max<int64_t>(b->npairs, 1) * sizeof(double)));
   QLB_CUDA(cudaMalloc((void **)&b->d_pair_ql, std::max<int64_t>(b->npairs, 1) * sizeof(int)));
   if (int rc = run_pair_prims(b)) return rc;

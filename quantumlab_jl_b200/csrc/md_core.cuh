@@ -28,41 +28,48 @@ __host__ __device__ constexpr int hidx(int L, int t, int u, int v) {
 // Table: rows T_i = i*BOYS_DT (i = 0..BOYS_NROW-1), columns m = 0..BOYS_NCOL-1 holding F_m(T_i).
 // F_L(T) by an 8-term Taylor expansion about the nearest row, lower orders by downward recursion;
 // beyond the table by the asymptotic F_0 and upward recursion (exp(-T) kept).  Accurate to ~1e-15 relative.
-constexpr int BOYS_NCOL = 24;           // supports total L <= 16
+constexpr int BOYS_NCOL = 24;           // columns 0..22: F_m(T_i) (total L <= 15); column 23: exp(-T_i)
+constexpr int BOYS_EXPCOL = BOYS_NCOL - 1;
 constexpr double BOYS_DT = 0.1;
 constexpr double BOYS_TMAX = 36.0;
 constexpr int BOYS_NROW = 362;          // rows 0..361 (T up to 36.1)
 
 template <int L>
 __device__ __forceinline__ void boys_array(double T, const double *__restrict__ tab, double *F) {
-  const double e = exp(-T);
   if (T < BOYS_TMAX) {
     const int i = (int)(T * (1.0 / BOYS_DT) + 0.5);
-    const double d = (double)i * BOYS_DT - T;  // T_i - T
-    const double *row = tab + i * BOYS_NCOL + L;
-    double f = __ldg(row + 7);
+    const double d = (double)i * BOYS_DT - T;  // T_i - T, |d| <= DT/2
+    const double *row = tab + i * BOYS_NCOL;
+    double f = __ldg(row + L + 7);
 #pragma unroll
-    for (int k = 6; k >= 0; --k) f = fma(f, d * (1.0 / (k + 1)), __ldg(row + k));
+    for (int k = 6; k >= 0; --k) f = fma(f, d * (1.0 / (k + 1)), __ldg(row + L + k));
     F[L] = f;
-    const double t2 = 2.0 * T;
+    if (L > 0) {
+      // exp(-T) = exp(-T_i) * exp(d): tabulated exp(-T_i) (last column) times a degree-8 Taylor polynomial (|d|<=0.05)
+      double e = 1.0 / 40320.0;
+      e = fma(e, d, 1.0 / 5040.0); e = fma(e, d, 1.0 / 720.0); e = fma(e, d, 1.0 / 120.0); e = fma(e, d, 1.0 / 24.0);
+      e = fma(e, d, 1.0 / 6.0); e = fma(e, d, 0.5); e = fma(e, d, 1.0); e = fma(e, d, 1.0);
+      e *= __ldg(row + BOYS_EXPCOL);
+      const double t2 = 2.0 * T;
 #pragma unroll
-    for (int m = L; m >= 1; --m) F[m - 1] = fma(t2, F[m], e) * (1.0 / (2 * m - 1));
+      for (int m = L; m >= 1; --m) F[m - 1] = fma(t2, F[m], e) * (1.0 / (2 * m - 1));
+    }
   } else {
     const double it = 1.0 / T;
     F[0] = 0.5 * sqrt(QLB_PI * it);
-    const double i2t = 0.5 * it;
+    if (L > 0) {
+      const double e = exp(-T);
+      const double i2t = 0.5 * it;
 #pragma unroll
-    for (int m = 0; m < L; ++m) F[m + 1] = fma((double)(2 * m + 1), F[m], -e) * i2t;
+      for (int m = 0; m < L; ++m) F[m + 1] = fma((double)(2 * m + 1), F[m], -e) * i2t;
+    }
   }
 }
 
 // ------------------------------------------------------------------ primitive-pair records (SoA in HBM)
+// one 48-byte record per primitive pair: {p, Px}, {Py, Pz}, {c_a c_b exp(-a b/p |AB|^2) / p, 1/(2p)}
 struct PrimPairs {
-  const double *__restrict__ p;   // exponent sum
-  const double *__restrict__ x;   // Gaussian product centre
-  const double *__restrict__ y;
-  const double *__restrict__ z;
-  const double *__restrict__ k;   // c_a c_b exp(-a b/p |AB|^2)
+  const double2 *__restrict__ rec;
 };
 
 struct PairRef {  // what one thread needs to know about one shell pair

@@ -59,7 +59,7 @@ struct qlb_basis {
   int *d_poff = nullptr, *d_boff = nullptr, *d_L = nullptr;
   int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pair_poff = nullptr, *d_pair_ql = nullptr;
   double *d_pair_Q = nullptr;
-  double *d_pp[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // p, x, y, z, k
+  double2 *d_pp = nullptr;  // 3 double2 per primitive pair: {p,Px} {Py,Pz} {k/p, 1/(2p)}
   int64_t nprimpairs = 0;
   // per-build scratch
   double *d_P = nullptr, *d_JK = nullptr, *d_H = nullptr;  // N*N, 2*N*N, N*N
