@@ -321,9 +321,24 @@ static int basis_build_pairs(qlb_basis *b) {
   // K3 (host part): sort each class by bound, descending; ties by original position (deterministic)
   std::vector<int> perm(b->npairs);
   std::iota(perm.begin(), perm.end(), 0);
-  for (int c = 0; c < NCLASS; ++c)
-    std::stable_sort(perm.begin() + b->class_off[c], perm.begin() + b->class_off[c + 1],
-                     [&](int x, int y) { return b->h_pair_Q[x] > b->h_pair_Q[y]; });
+  auto kbin = [&](int x) {
+    const int K = b->h_nprim[b->h_pair_a[x]] * b->h_nprim[b->h_pair_b[x]];
+    return K <= 1 ? 0 : K <= 4 ? 1 : K <= 12 ? 2 : K <= 36 ? 3 : 4;
+  };
+  b->seg_off.clear();
+  b->seg_cls.clear();
+  for (int c = 0; c < NCLASS; ++c) {
+    std::stable_sort(perm.begin() + b->class_off[c], perm.begin() + b->class_off[c + 1], [&](int x, int y) {
+      const int kx = kbin(x), ky = kbin(y);
+      return kx != ky ? kx > ky : b->h_pair_Q[x] > b->h_pair_Q[y];
+    });
+    for (int i = b->class_off[c]; i < b->class_off[c + 1]; ++i)
+      if (i == b->class_off[c] || kbin(perm[i]) != kbin(perm[i - 1])) {
+        b->seg_off.push_back(i);
+        b->seg_cls.push_back(c);
+      }
+  }
+  b->seg_off.push_back((int)b->npairs);
   std::vector<int> na(b->npairs), nb(b->npairs);
   std::vector<double> nq(b->npairs);
   b->h_pair_ql.resize(b->npairs);
@@ -442,9 +457,19 @@ static void base_params(qlb_basis *b, ClassParams &prm) {
   prm.nranks = 1;
 }
 
-// number of leading pairs of class c (sorted by bound, descending) with ql >= need
-static int prefix_count(const qlb_basis *b, int c, int need) {
-  const int *lo = b->h_pair_ql.data() + b->class_off[c], *hi = b->h_pair_ql.data() + b->class_off[c + 1];
+// kernels launched per class-pair launch (split classes launch one kernel per ket-d component)
+static int launch_count_of(int X, int Y) {
+  int la, lb, lc, ld;
+  class_L(X, la, lb);
+  class_L(Y, lc, ld);
+  const int L = la + lb + lc + ld;
+  const bool split = (L >= 6) && ld >= 1;  // (dp|dp) (dd|pp) (dd|dp) (dd|dd): see the Makefile policy table
+  return split ? ncart(ld) : 1;
+}
+
+// number of leading pairs of segment sg (sorted by bound, descending) with ql >= need
+static int prefix_count(const qlb_basis *b, int sg, int need) {
+  const int *lo = b->h_pair_ql.data() + b->seg_off[sg], *hi = b->h_pair_ql.data() + b->seg_off[sg + 1];
   // descending order: first position with ql < need
   return (int)(std::partition_point(lo, hi, [need](int q) { return q >= need; }) - lo);
 }
@@ -480,11 +505,12 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
   QLB_CUDA(cudaMemsetAsync(dJ, 0, N2 * sizeof(double), s));
   QLB_CUDA(cudaMemsetAsync(dK, 0, N2 * sizeof(double), s));
   QLB_CUDA(cudaMemsetAsync(b->d_counters, 0, 2 * NQCLASS * sizeof(unsigned long long), s));
-  int nsig[NCLASS];
+  const int nseg = (int)b->seg_cls.size();
+  std::vector<int> nsig(nseg);
   int64_t pairs_sig = 0;
-  for (int c = 0; c < NCLASS; ++c) {
-    nsig[c] = screen ? prefix_count(b, c, tlog - b->qlmax - dlmax) : b->class_off[c + 1] - b->class_off[c];
-    pairs_sig += nsig[c];
+  for (int sg = 0; sg < nseg; ++sg) {
+    nsig[sg] = screen ? prefix_count(b, sg, tlog - b->qlmax - dlmax) : b->seg_off[sg + 1] - b->seg_off[sg];
+    pairs_sig += nsig[sg];
   }
   ClassParams prm;
   base_params(b, prm);
@@ -492,30 +518,45 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
   prm.rank = rank; prm.nranks = nranks;
   prm.P = dP; prm.J = dJ; prm.K = dK;
   if (stats) cudaEventRecord(b->ev[1], s);
-  for (int X = NCLASS - 1; X >= 0; --X)  // heaviest classes first
-    for (int Y = X; Y >= 0; --Y) {
+  bool qc_started[NQCLASS] = {false};
+  // heaviest classes first; within a class pair, every (bra segment, ket segment) combination is one launch
+  int cls_seg[NCLASS + 1];  // segment range of each class
+  for (int c = 0, sg = 0; c <= NCLASS; ++c) {
+    while (sg < nseg && b->seg_cls[sg] < c) ++sg;
+    cls_seg[c] = sg;
+  }
+  for (int X = NCLASS - 1; X >= 0; --X)
+   for (int Y = X; Y >= 0; --Y)
+    for (int sx = cls_seg[X + 1] - 1; sx >= cls_seg[X]; --sx)
+     for (int sy = (X == Y ? sx : cls_seg[Y + 1] - 1); sy >= cls_seg[Y]; --sy) {
       const int qc = qclass_of(X, Y);
-      if (nsig[X] == 0 || nsig[Y] == 0) continue;
-      prm.bra_off = b->class_off[X]; prm.bra_n = nsig[X];
-      prm.ket_off = b->class_off[Y]; prm.ket_n = nsig[Y];
-      prm.same = (X == Y) ? 1 : 0;
-      int ket_eff = nsig[Y];
-      if (screen) ket_eff = std::min(ket_eff, prefix_count(b, Y, tlog - dlmax - b->h_pair_ql[b->class_off[X]]));
+      if (nsig[sx] == 0 || nsig[sy] == 0) continue;
+      prm.bra_off = b->seg_off[sx]; prm.bra_n = nsig[sx];
+      prm.ket_off = b->seg_off[sy]; prm.ket_n = nsig[sy];
+      prm.same = (sx == sy) ? 1 : 0;
+      int ket_eff = nsig[sy];
+      if (screen) ket_eff = std::min(ket_eff, prefix_count(b, sy, tlog - dlmax - b->h_pair_ql[b->seg_off[sx]]));
       if (ket_eff == 0) continue;
-      const int nrows = (prm.bra_n + TILE_BRA - 1) / TILE_BRA;
-      const int nrows_local = rank < nrows ? (nrows - rank + nranks - 1) / nranks : 0;
-      if (nrows_local == 0) continue;
-      prm.nbx = (ket_eff + TILE_KET - 1) / TILE_KET;
-      const int64_t grid = (int64_t)nrows_local * prm.nbx;
+      if (prm.same) ket_eff = std::min(ket_eff, prm.bra_n);
+      // one CTA per (bra pair, chunk of kc candidate kets); larger chunks waste fewer lanes in the final drain,
+      // smaller ones give more CTAs: keep at least ~32 CTAs per SM when the class is big enough
+      int kc = 8192;
+      while (kc > 1024 && (int64_t)prm.bra_n * ((ket_eff + kc - 1) / kc) < (int64_t)e.sm_count * 32) kc >>= 1;
+      prm.kc = kc;
+      prm.nchunk = (ket_eff + kc - 1) / kc;
+      const int64_t nblocks = (int64_t)prm.bra_n * prm.nchunk;
+      const int64_t grid = rank < nblocks ? (nblocks - rank + nranks - 1) / nranks : 0;
+      if (grid == 0) continue;
       if (grid > 0x7fffffffLL) {
         set_error("qlb_build_jk_device: grid too large");
         return QLB_ERR_ARG;
       }
       prm.counters = b->d_counters + 2 * qc;
-      if (prof) cudaEventRecord(b->ev[4 + 2 * qc], s);
+      if (prof && !qc_started[qc]) cudaEventRecord(b->ev[4 + 2 * qc], s);
+      qc_started[qc] = true;
       if (int ce = launch_class_kernel(X, Y, 0, (unsigned)grid, s, prm)) return cuda_fail((cudaError_t)ce, "eri_class_kernel");
       if (prof) cudaEventRecord(b->ev[4 + 2 * qc + 1], s);
-      ++launches;
+      launches += launch_count_of(X, Y);
     }
   if (stats) {
     cudaEventRecord(b->ev[2], s);

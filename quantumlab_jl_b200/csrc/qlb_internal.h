@@ -53,6 +53,9 @@ struct qlb_basis {
   std::vector<int> h_pair_a, h_pair_b, h_pair_poff, h_pair_ql;
   std::vector<double> h_pair_Q;
   int class_off[qlb::NCLASS + 1] = {0};
+  // segments: each class is split by contraction degree (primitive pairs per shell pair) so that the threads of a
+  // warp run primitive loops of similar length; every segment is sorted by Schwarz bound, descending
+  std::vector<int> seg_off, seg_cls;
   int qlmax = -32768;
   // device
   double *d_xyz = nullptr, *d_exps = nullptr, *d_coefs = nullptr;

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqlb200.so")
+LIB_PATH = os.environ.get("QLB200_LIB", os.path.join(_HERE, "libqlb200.so"))
 NQCLASS = 21
 NCLASS = 6
 CLASS_NAMES = ("ss", "ps", "pp", "ds", "dp", "dd")
