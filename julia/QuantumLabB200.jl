@@ -1,0 +1,153 @@
+# QuantumLabB200.jl -- thin Julia host side of libqlb200.so (include/qlb200.h).
+#
+# This is the binding a QuantumLab.jl maintainer adds next to LibInt2Module.jl (the reference's existing FFI seam,
+# src/SubModules/LibInt2Module.jl:30-40, 62-110, 193-334): a third shell-vector type, `B200Shells`, on which the
+# hot-path methods dispatch.  It is deliberately thin -- every line maps 1:1 onto the ctypes harness in
+# quantumlab_jl_b200/{libqlb,b200shells}.py, which IS executed by the test-suite (no Julia exists in the build image,
+# so this file cannot be run there; see INTEGRATION.md).
+module QuantumLabB200
+
+using Libdl
+using ..BaseModule, ..ShellModule, ..GeometryModule
+import ..SpecialMatricesModule: computeMatrixCoulomb, computeMatrixExchange, computeMatrixFock,
+                                computeTensorElectronRepulsionIntegrals, computeTensorBlockElectronRepulsionIntegrals,
+                                computeMatrixOverlap, computeMatrixKinetic, computeMatrixNuclearAttraction
+import ..HartreeFockModule: evaluateSCF
+
+export B200Shells, destroy!
+
+const libqlb = Ref{Ptr{Nothing}}(C_NULL)
+
+function __init__()
+  # same pattern as LibInt2Module.__init__ (LibInt2Module.jl:30-40); unlike libint2 a load failure is an ERROR:
+  # there is no stub / CPU fallback for this backend.
+  push!(Libdl.DL_LOAD_PATH, joinpath(@__DIR__, "..", "deps", "usr", "lib"))
+  libqlb[] = Libdl.dlopen("libqlb200")
+  check(ccall(dlsym(libqlb[], :qlb_init), Cint, (Cint,), -1))
+end
+
+lasterror() = unsafe_string(ccall(dlsym(libqlb[], :qlb_last_error), Cstring, ()))
+check(rc::Integer) = rc == 0 ? nothing : error("libqlb200 error $rc: $(lasterror())")
+
+"Per-build statistics, layout of `struct qlb_stats` (include/qlb200.h)."
+mutable struct QlbStats
+  quartets_unique::Int64; quartets_kept::Int64
+  quartets_kept_class::NTuple{21,Int64}; prim_quartets_class::NTuple{21,Int64}
+  pairs_total::Int64; pairs_significant::Int64
+  ms_total::Float64; ms_eri::Float64; ms_class::NTuple{21,Float64}
+  flops_algorithmic::Float64; kernel_launches::Int32; reserved::Int32
+  QlbStats() = new(0, 0, ntuple(_ -> 0, 21), ntuple(_ -> 0, 21), 0, 0, 0.0, 0.0, ntuple(_ -> 0.0, 21), 0.0, 0, 0)
+end
+
+"""
+    B200Shells(shells::Vector{Shell}; tau=1e-12)
+Device-resident shell list: the analogue of `Vector{LibInt2Shell}` + `LibInt2EngineCoulomb` (LibInt2Module.jl:62-68,
+193-204).  Owns an opaque `qlb_basis*`; freed by `destroy!` (LibInt2Module.jl:108-110) or the finalizer.
+Coefficients are passed as the Shell constructor leaves them (ShellModule.jl:25-48).
+"""
+mutable struct B200Shells <: AbstractVector{Shell}
+  shells::Vector{Shell}
+  handle::Ptr{Nothing}
+  nbf::Int
+  tau::Float64
+  cacheP::Union{Nothing,Matrix{Float64}}
+  cacheJ::Matrix{Float64}
+  cacheK::Matrix{Float64}
+  function B200Shells(shells::Vector{Shell}; tau::Float64=1e-12)
+    centers = Float64[c for sh in shells for c in (sh.center.x, sh.center.y, sh.center.z)]
+    L       = Int32[sh.lqn.exponent for sh in shells]
+    nprim   = Int32[length(sh.exponents) for sh in shells]
+    exps    = vcat([sh.exponents for sh in shells]...)
+    coefs   = vcat([sh.coefficients for sh in shells]...)
+    h = Ref{Ptr{Nothing}}(C_NULL)
+    check(ccall(dlsym(libqlb[], :qlb_basis_create), Cint,
+                (Cint, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Ptr{Nothing}}),
+                length(shells), centers, L, nprim, exps, coefs, h))
+    n = mapreduce(nbf, +, shells)
+    obj = new(shells, h[], n, tau, nothing, zeros(0, 0), zeros(0, 0))
+    finalizer(destroy!, obj)
+    obj
+  end
+end
+Base.size(b::B200Shells) = size(b.shells)
+Base.getindex(b::B200Shells, i::Int) = b.shells[i]
+
+function destroy!(b::B200Shells)
+  if b.handle != C_NULL
+    ccall(dlsym(libqlb[], :qlb_basis_destroy), Cint, (Ptr{Nothing},), b.handle)
+    b.handle = C_NULL
+  end
+end
+
+"One fused, screened pass: (J, K) as SpecialMatricesModule.jl:33-100 defines them."
+function buildJK(b::B200Shells, P::Matrix{Float64}; stats::Union{Nothing,QlbStats}=nothing)
+  size(P) == (b.nbf, b.nbf) || error("density matrix must be $(b.nbf)x$(b.nbf)")
+  J = Matrix{Float64}(undef, b.nbf, b.nbf); K = similar(J)
+  st = stats === nothing ? C_NULL : pointer_from_objref(stats)
+  check(ccall(dlsym(libqlb[], :qlb_build_jk), Cint,
+              (Ptr{Nothing}, Ptr{Float64}, Cdouble, Ptr{Float64}, Ptr{Float64}, Ptr{Nothing}),
+              b.handle, P, b.tau, J, K, st))
+  J, K
+end
+
+# `coulomb(P)` followed by `exchange(P)` (HartreeFockModule.jl:123-131) costs ONE device pass: same P => cached
+function jkcached(b::B200Shells, P::Matrix{Float64})
+  if b.cacheP === nothing || b.cacheP != P
+    b.cacheJ, b.cacheK = buildJK(b, P)
+    b.cacheP = copy(P)
+  end
+  b.cacheJ, b.cacheK
+end
+
+computeMatrixCoulomb(b::B200Shells, density::Matrix)  = copy(jkcached(b, Matrix{Float64}(density))[1])   # :231-244
+computeMatrixExchange(b::B200Shells, density::Matrix) = copy(jkcached(b, Matrix{Float64}(density))[2])   # :268-281
+
+function onee(b::B200Shells, sym::Symbol)
+  M = Matrix{Float64}(undef, b.nbf, b.nbf)
+  check(ccall(dlsym(libqlb[], sym), Cint, (Ptr{Nothing}, Ptr{Float64}), b.handle, M))
+  M
+end
+computeMatrixOverlap(b::B200Shells) = onee(b, :qlb_overlap)                                              # :102-125
+computeMatrixKinetic(b::B200Shells) = onee(b, :qlb_kinetic)                                              # :127-150
+function computeMatrixNuclearAttraction(b::B200Shells, geo::Geometry)                                    # :152-177
+  xyz = Float64[c for a in geo.atoms for c in (a.position.x, a.position.y, a.position.z)]
+  Z   = Float64[a.element.atomicNumber for a in geo.atoms]
+  V = Matrix{Float64}(undef, b.nbf, b.nbf)
+  check(ccall(dlsym(libqlb[], :qlb_nuclear_attraction), Cint, (Ptr{Nothing}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+              b.handle, length(Z), xyz, Z, V))
+  V
+end
+
+function computeMatrixFock(b::B200Shells, geo::Geometry, density::Matrix)                                # :292-303
+  H = computeMatrixKinetic(b) + computeMatrixNuclearAttraction(b, geo)
+  F = similar(H)
+  check(ccall(dlsym(libqlb[], :qlb_fock), Cint,
+              (Ptr{Nothing}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}, Ptr{Nothing}),
+              b.handle, H, Matrix{Float64}(density), b.tau, F, C_NULL))
+  F
+end
+
+function computeTensorElectronRepulsionIntegrals(b::B200Shells)                                          # :198-207
+  T = Array{Float64,4}(undef, b.nbf, b.nbf, b.nbf, b.nbf)
+  check(ccall(dlsym(libqlb[], :qlb_eri_tensor), Cint, (Ptr{Nothing}, Ptr{Float64}), b.handle, T))
+  T
+end
+
+"Block of one shell quartet, 1-based shell indices into `b` (SpecialMatricesModule.jl:184-186, LibInt2Module.jl:319-334)."
+function computeTensorBlockElectronRepulsionIntegrals(b::B200Shells, i::Int, j::Int, k::Int, l::Int)
+  blk = Array{Float64,4}(undef, nbf(b[i]), nbf(b[j]), nbf(b[k]), nbf(b[l]))
+  check(ccall(dlsym(libqlb[], :qlb_eri_block), Cint, (Ptr{Nothing}, Cint, Cint, Cint, Cint, Ptr{Float64}),
+              b.handle, i - 1, j - 1, k - 1, l - 1, blk))
+  blk
+end
+
+# evaluateSCF(basis::B200Shells, geometry, guess, nocc): the convenience form (HartreeFockModule.jl:158-208) with the
+# integral-direct closures of its libint branch (:197-199,207); iteration semantics untouched.
+function evaluateSCF(b::B200Shells, geometry::Geometry, initialGuessDensity, electronNumber::Integer; kwargs...)
+  S = computeMatrixOverlap(b); T = computeMatrixKinetic(b); V = computeMatrixNuclearAttraction(b, geometry)
+  Pinit = InitialGuessModule.computeDensityMatrixGuess(initialGuessDensity, size(S)[1])
+  Vnn = computeEnergyInteratomicRepulsion(geometry)
+  evaluateSCF(Pinit, S, T, V, P -> computeMatrixCoulomb(b, P), P -> computeMatrixExchange(b, P), Vnn, electronNumber; kwargs...)
+end
+
+end # module

@@ -323,7 +323,8 @@ static int basis_build_pairs(qlb_basis *b) {
   std::iota(perm.begin(), perm.end(), 0);
   auto kbin = [&](int x) {
     const int K = b->h_nprim[b->h_pair_a[x]] * b->h_nprim[b->h_pair_b[x]];
-    return K <= 1 ? 0 : K <= 4 ? 1 : K <= 12 ? 2 : K <= 36 ? 3 : 4;
+    (void)K;
+    return 0;  // binning by contraction degree measured no gain (the Schwarz ordering already clusters similar K)
   };
   b->seg_off.clear();
   b->seg_cls.clear();
@@ -463,7 +464,7 @@ static int launch_count_of(int X, int Y) {
   class_L(X, la, lb);
   class_L(Y, lc, ld);
   const int L = la + lb + lc + ld;
-  const bool split = (L >= 6) && ld >= 1;  // (dp|dp) (dd|pp) (dd|dp) (dd|dd): see the Makefile policy table
+  const bool split = (L >= 5) && ld >= 1;  // (dp|pp) (dp|dp) (dd|pp) (dd|dp) (dd|dd): see the Makefile policy table
   return split ? ncart(ld) : 1;
 }
 
@@ -538,15 +539,11 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       if (screen) ket_eff = std::min(ket_eff, prefix_count(b, sy, tlog - dlmax - b->h_pair_ql[b->seg_off[sx]]));
       if (ket_eff == 0) continue;
       if (prm.same) ket_eff = std::min(ket_eff, prm.bra_n);
-      // one CTA per (bra pair, chunk of kc candidate kets); larger chunks waste fewer lanes in the final drain,
-      // smaller ones give more CTAs: keep at least ~32 CTAs per SM when the class is big enough
-      int kc = 8192;
-      while (kc > 1024 && (int64_t)prm.bra_n * ((ket_eff + kc - 1) / kc) < (int64_t)e.sm_count * 32) kc >>= 1;
-      prm.kc = kc;
-      prm.nchunk = (ket_eff + kc - 1) / kc;
-      const int64_t nblocks = (int64_t)prm.bra_n * prm.nchunk;
-      const int64_t grid = rank < nblocks ? (nblocks - rank + nranks - 1) / nranks : 0;
-      if (grid == 0) continue;
+      const int nrows = (prm.bra_n + TILE_BRA - 1) / TILE_BRA;
+      const int nrows_local = rank < nrows ? (nrows - rank + nranks - 1) / nranks : 0;
+      if (nrows_local == 0) continue;
+      prm.nbx = (ket_eff + TILE_KET - 1) / TILE_KET;
+      const int64_t grid = (int64_t)nrows_local * prm.nbx;
       if (grid > 0x7fffffffLL) {
         set_error("qlb_build_jk_device: grid too large");
         return QLB_ERR_ARG;
