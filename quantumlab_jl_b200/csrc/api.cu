@@ -539,11 +539,16 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       if (screen) ket_eff = std::min(ket_eff, prefix_count(b, sy, tlog - dlmax - b->h_pair_ql[b->seg_off[sx]]));
       if (ket_eff == 0) continue;
       if (prm.same) ket_eff = std::min(ket_eff, prm.bra_n);
-      const int nrows = (prm.bra_n + TILE_BRA - 1) / TILE_BRA;
-      const int nrows_local = rank < nrows ? (nrows - rank + nranks - 1) / nranks : 0;
-      if (nrows_local == 0) continue;
-      prm.nbx = (ket_eff + TILE_KET - 1) / TILE_KET;
-      const int64_t grid = (int64_t)nrows_local * prm.nbx;
+      // one warp task per (bra pair, chunk of kc candidate kets).  Large chunks waste fewer lanes in the final partial
+      // drain; small ones give more tasks: aim for >= 64 warp tasks per SM while the class is big enough
+      int kc = 4096;
+      while (kc > 128 && (int64_t)prm.bra_n * ((ket_eff + kc - 1) / kc) < (int64_t)e.sm_count * 64) kc >>= 1;
+      prm.kc = kc;
+      prm.nchunk = (ket_eff + kc - 1) / kc;
+      const int64_t ntasks = (int64_t)prm.bra_n * prm.nchunk;
+      const int64_t mytasks = rank < ntasks ? (ntasks - rank + nranks - 1) / nranks : 0;
+      if (mytasks == 0) continue;
+      const int64_t grid = (mytasks + 3) / 4;  // WT_WARPS warp tasks per CTA
       if (grid > 0x7fffffffLL) {
         set_error("qlb_build_jk_device: grid too large");
         return QLB_ERR_ARG;

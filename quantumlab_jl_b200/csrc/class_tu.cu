@@ -17,11 +17,10 @@ namespace qlb {
 #ifdef QC_DSEL
 // ---- one ket-d component of a split class
 int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, QC_DSEL)(unsigned grid, cudaStream_t s, const ClassParams &prm) {
-  const dim3 block(TILE_KET, TILE_BRA);
 #if QC_UNR
-  unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, 1, QC_DSEL><<<grid, block, 0, s>>>(prm);
+  unr::eri_jk_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, QC_DSEL><<<grid, 32 * unr::WT_WARPS, 0, s>>>(prm);
 #else
-  rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, 1, QC_DSEL><<<grid, block, 0, s>>>(prm);
+  rol::eri_jk_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, QC_DSEL><<<grid, 32 * rol::WT_WARPS, 0, s>>>(prm);
 #endif
   return (int)cudaGetLastError();
 }
@@ -51,9 +50,9 @@ int QC_CAT(QC_LA, QC_LB, QC_LC, QC_LD)(int mode, unsigned grid, cudaStream_t s, 
 #endif
     return rc;
 #elif QC_UNR
-    unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, QC_DSTEP><<<grid, block, 0, s>>>(prm);
+    unr::eri_jk_kernel<QC_LA, QC_LB, QC_LC, QC_LD, QC_DSTEP><<<grid, 32 * unr::WT_WARPS, 0, s>>>(prm);
 #else
-    rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, QC_DSTEP><<<grid, block, 0, s>>>(prm);
+    rol::eri_jk_kernel<QC_LA, QC_LB, QC_LC, QC_LD, QC_DSTEP><<<grid, 32 * rol::WT_WARPS, 0, s>>>(prm);
 #endif
   } else {
     rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, ncart(QC_LD)><<<grid, block, 0, s>>>(prm);
