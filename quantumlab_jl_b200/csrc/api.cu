@@ -184,6 +184,9 @@ extern "C" int qlb_init(int device) {
   e.device = device;
   e.sm_count = prop.multiProcessorCount;
   QLB_CUDA(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
+  QLB_CUDA(cudaStreamCreateWithFlags(&e.side_stream, cudaStreamNonBlocking));
+  QLB_CUDA(cudaEventCreateWithFlags(&e.ev_fork, cudaEventDisableTiming));
+  QLB_CUDA(cudaEventCreateWithFlags(&e.ev_join, cudaEventDisableTiming));
   std::vector<double> tab;
   make_boys_table(tab);
   QLB_CUDA(cudaMalloc((void **)&e.d_boys, tab.size() * sizeof(double)));
@@ -201,6 +204,9 @@ extern "C" int qlb_finalize(void) {
   cudaSetDevice(e.device);
   if (e.d_boys) cudaFree(e.d_boys);
   if (e.stream) cudaStreamDestroy(e.stream);
+  if (e.side_stream) cudaStreamDestroy(e.side_stream);
+  if (e.ev_fork) cudaEventDestroy(e.ev_fork);
+  if (e.ev_join) cudaEventDestroy(e.ev_join);
   e = Engine();
   return QLB_OK;
 }
@@ -520,6 +526,7 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
   prm.P = dP; prm.J = dJ; prm.K = dK;
   if (stats) cudaEventRecord(b->ev[1], s);
   bool qc_started[NQCLASS] = {false};
+  bool forked = false;
   // heaviest classes first; within a class pair, every (bra segment, ket segment) combination is one launch
   int cls_seg[NCLASS + 1];  // segment range of each class
   for (int c = 0, sg = 0; c <= NCLASS; ++c) {
@@ -539,16 +546,11 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       if (screen) ket_eff = std::min(ket_eff, prefix_count(b, sy, tlog - dlmax - b->h_pair_ql[b->seg_off[sx]]));
       if (ket_eff == 0) continue;
       if (prm.same) ket_eff = std::min(ket_eff, prm.bra_n);
-      // one warp task per (bra pair, chunk of kc candidate kets).  Large chunks waste fewer lanes in the final partial
-      // drain; small ones give more tasks: aim for >= 64 warp tasks per SM while the class is big enough
-      int kc = 4096;
-      while (kc > 128 && (int64_t)prm.bra_n * ((ket_eff + kc - 1) / kc) < (int64_t)e.sm_count * 64) kc >>= 1;
-      prm.kc = kc;
-      prm.nchunk = (ket_eff + kc - 1) / kc;
-      const int64_t ntasks = (int64_t)prm.bra_n * prm.nchunk;
-      const int64_t mytasks = rank < ntasks ? (ntasks - rank + nranks - 1) / nranks : 0;
-      if (mytasks == 0) continue;
-      const int64_t grid = (mytasks + 3) / 4;  // WT_WARPS warp tasks per CTA
+      const int nrows = (prm.bra_n + TILE_BRA - 1) / TILE_BRA;
+      const int nrows_local = rank < nrows ? (nrows - rank + nranks - 1) / nranks : 0;
+      if (nrows_local == 0) continue;
+      prm.nbx = (ket_eff + TILE_KET - 1) / TILE_KET;
+      const int64_t grid = (int64_t)nrows_local * prm.nbx;
       if (grid > 0x7fffffffLL) {
         set_error("qlb_build_jk_device: grid too large");
         return QLB_ERR_ARG;
@@ -556,10 +558,25 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       prm.counters = b->d_counters + 2 * qc;
       if (prof && !qc_started[qc]) cudaEventRecord(b->ev[4 + 2 * qc], s);
       qc_started[qc] = true;
-      if (int ce = launch_class_kernel(X, Y, 0, (unsigned)grid, s, prm)) return cuda_fail((cudaError_t)ce, "eri_class_kernel");
+      // (dd|dd) has few quartets, each with a long serial body: it cannot fill the GPU, so it runs on a side stream
+      // concurrently with the rest of the classes (all classes only add into J/K with atomics)
+      cudaStream_t ls = s;
+      if (!prof && X == NCLASS - 1 && Y == NCLASS - 1) {
+        if (!forked) {
+          QLB_CUDA(cudaEventRecord(e.ev_fork, s));
+          QLB_CUDA(cudaStreamWaitEvent(e.side_stream, e.ev_fork, 0));
+          forked = true;
+        }
+        ls = e.side_stream;
+      }
+      if (int ce = launch_class_kernel(X, Y, 0, (unsigned)grid, ls, prm)) return cuda_fail((cudaError_t)ce, "eri_class_kernel");
       if (prof) cudaEventRecord(b->ev[4 + 2 * qc + 1], s);
       launches += launch_count_of(X, Y);
     }
+  if (forked) {
+    QLB_CUDA(cudaEventRecord(e.ev_join, e.side_stream));
+    QLB_CUDA(cudaStreamWaitEvent(s, e.ev_join, 0));
+  }
   if (stats) {
     cudaEventRecord(b->ev[2], s);
     unsigned long long h[2 * NQCLASS];

@@ -67,7 +67,6 @@ struct ClassParams {
   int tlog, dlmax, screen;
   // sharding of bra tile rows over ranks, grid decoding
   int rank, nranks, nbx;
-  int kc, nchunk;                      // eri_jk_kernel: candidate kets per warp task, tasks per bra row
   // data
   const double *__restrict__ P;
   double *J, *K;

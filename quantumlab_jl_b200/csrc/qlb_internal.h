@@ -26,6 +26,8 @@ struct Engine {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side_stream = nullptr;  // sparsely populated classes run beside the main sequence
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double *d_boys = nullptr;
   bool profiling = false;
   // NCCL (loaded lazily with dlopen)
