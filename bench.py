@@ -204,6 +204,10 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL's version banner) write to fd 1: keep stdout clean for the single JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
@@ -274,6 +278,14 @@ def run_ours(args):
         dist.all_reduce(flops)
     F_dev = dF.cpu().numpy().reshape(N, N)
     check_err = float(np.abs(F_dev - F_dev.T).max())
+    shard_err = 0.0
+    if world > 1:
+        # sharded + all-reduced build against the same build done by this rank alone (rank 0 of 1)
+        libqlb.check(lib.qlb_build_jk_device(h, C.c_void_p(dP.data_ptr()), args.tau, pJ, pK, 0, 1, sptr, None))
+        libqlb.check(lib.qlb_symmetrize_device(h, pJ, pK, sptr))
+        libqlb.check(lib.qlb_fock_device(h, C.c_void_p(dH.data_ptr()), pJ, pK, C.c_void_p(dF.data_ptr()), sptr))
+        torch.cuda.synchronize()
+        shard_err = float(np.abs(dF.cpu().numpy().reshape(N, N) - F_dev).max())
 
     # ---- timed region 1: device resident
     for _ in range(args.warmup):
@@ -362,7 +374,7 @@ def run_ours(args):
                          "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "algorithmic_flops_per_build": tot_flops, "hbm_gbs_measured": peaks.get("hbm_gbs"),
                          "per_class": per_class},
-            "fock_symmetry_residual": check_err,
+            "fock_symmetry_residual": check_err, "sharded_vs_single_rank_max_abs_diff": shard_err,
         }
         # CPU baselines on this box's host cores (bounded samples)
         try:
@@ -375,7 +387,10 @@ def run_ours(args):
                                          "sample": descf + "; McMurchie-Davidson, 8-fold symmetry, same screening, OpenMP"}
         except Exception as exc:  # the oracle is test infrastructure: its absence must not hide the GPU number
             line["cpu_baseline"] = {"error": repr(exc)}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         lib.qlb_comm_destroy()
