@@ -9,7 +9,6 @@
 #include <algorithm>
 #include <numeric>
 
-#define QLB_DEFINE_SCREEN_KERNEL
 #include "qlb_internal.h"
 
 namespace qlb {
@@ -25,10 +24,12 @@ int cuda_fail(cudaError_t e, const char *what) {
 
 // ------------------------------------------------------------------ Boys table (host, long double series)
 static void make_boys_table(std::vector<double> &tab) {
-  tab.assign((size_t)BOYS_NROW * BOYS_NCOL, 0.0);
+  // layout [L][row][BOYS_ROWLEN]: F_L..F_{L+7}(T_i), exp(-T_i), pad   (md_core.cuh)
+  tab.assign((size_t)(BOYS_LMAX + 1) * BOYS_TABLE_DOUBLES, 0.0);
+  const int mtop = BOYS_LMAX + 7;
+  std::vector<long double> F(mtop + 1);
   for (int i = 0; i < BOYS_NROW; ++i) {
     const long double T = (long double)i * (long double)BOYS_DT;
-    const int mtop = BOYS_NCOL - 2;
     // F_mtop(T) = exp(-T) sum_k (2T)^k / ((2m+1)(2m+3)...(2m+2k+1)), then downward recursion
     long double term = 1.0L / (2 * mtop + 1), sum = term;
     for (int k = 1; k < 2000; ++k) {
@@ -37,13 +38,13 @@ static void make_boys_table(std::vector<double> &tab) {
       if (term < 1e-22L * sum) break;
     }
     const long double ex = expl(-T);
-    long double F = ex * sum;
-    tab[(size_t)i * BOYS_NCOL + mtop] = (double)F;
-    for (int m = mtop; m > 0; --m) {
-      F = (2.0L * T * F + ex) / (2 * m - 1);
-      tab[(size_t)i * BOYS_NCOL + m - 1] = (double)F;
+    F[mtop] = ex * sum;
+    for (int m = mtop; m > 0; --m) F[m - 1] = (2.0L * T * F[m] + ex) / (2 * m - 1);
+    for (int L = 0; L <= BOYS_LMAX; ++L) {
+      double *row = tab.data() + (size_t)L * BOYS_TABLE_DOUBLES + (size_t)i * BOYS_ROWLEN;
+      for (int k = 0; k < 8; ++k) row[k] = (double)F[L + k];
+      row[8] = (double)ex;
     }
-    tab[(size_t)i * BOYS_NCOL + BOYS_EXPCOL] = (double)ex;
   }
 }
 
@@ -113,8 +114,6 @@ __global__ void dfma_probe_kernel(double *out, int iters) {
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
-
-constexpr int LIST_SLOTS = 4096;  // screening launches per build (class pairs x row batches)
 
 static int require_ready() {
   if (!g_engine.ready) {
@@ -270,7 +269,7 @@ extern "C" int qlb_basis_destroy(qlb_basis *b) {
   if (g_engine.ready) cudaSetDevice(g_engine.device);
   void *ptrs[] = {b->d_xyz, b->d_exps, b->d_coefs, b->d_poff, b->d_boff, b->d_L, b->d_pair_a, b->d_pair_b,
                   b->d_pair_poff, b->d_pair_ql, b->d_pair_Q, b->d_pp,
-                  b->d_P, b->d_JK, b->d_H, b->d_dl, b->d_counters, b->d_list, b->d_list_counts};
+                  b->d_P, b->d_JK, b->d_H, b->d_dl, b->d_counters};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (auto &ev : b->ev)
@@ -426,17 +425,6 @@ extern "C" int qlb_basis_create(int nsh, const double *centers, const int32_t *L
     return cuda_fail(ce, "cudaMalloc(scratch)");
   }
   for (auto &ev : b->ev) cudaEventCreate(&ev);
-  {
-    // compact quartet list: 8 B per surviving quartet of one screening launch; big class pairs are batched by rows
-    const double np2 = 0.5 * (double)nsh * (nsh + 1);
-    const double want = std::min(256.0 * 1024 * 1024, std::max(1024.0 * 1024, np2 * np2 / 2));
-    b->list_cap = (size_t)want;
-    if ((ce = cudaMalloc((void **)&b->d_list, b->list_cap * sizeof(int2))) != cudaSuccess ||
-        (ce = cudaMalloc((void **)&b->d_list_counts, LIST_SLOTS * sizeof(unsigned))) != cudaSuccess) {
-      qlb_basis_destroy(b);
-      return cuda_fail(ce, "cudaMalloc(list)");
-    }
-  }
   if ((rc = basis_build_pairs(b))) {
     qlb_basis_destroy(b);
     return rc;
@@ -526,7 +514,6 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
   QLB_CUDA(cudaMemsetAsync(dJ, 0, N2 * sizeof(double), s));
   QLB_CUDA(cudaMemsetAsync(dK, 0, N2 * sizeof(double), s));
   QLB_CUDA(cudaMemsetAsync(b->d_counters, 0, 2 * NQCLASS * sizeof(unsigned long long), s));
-  QLB_CUDA(cudaMemsetAsync(b->d_list_counts, 0, LIST_SLOTS * sizeof(unsigned), s));
   const int nseg = (int)b->seg_cls.size();
   std::vector<int> nsig(nseg);
   int64_t pairs_sig = 0;
@@ -542,9 +529,6 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
   if (stats) cudaEventRecord(b->ev[1], s);
   bool qc_started[NQCLASS] = {false};
   bool forked = false;
-  int list_slot = 0;
-  std::vector<int> slot_qc;
-  slot_qc.reserve(64);
   // heaviest classes first; within a class pair, every (bra segment, ket segment) combination is one launch
   int cls_seg[NCLASS + 1];  // segment range of each class
   for (int c = 0, sg = 0; c <= NCLASS; ++c) {
@@ -568,6 +552,10 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       const int nrows_local = rank < nrows ? (nrows - rank + nranks - 1) / nranks : 0;
       if (nrows_local == 0) continue;
       prm.nbx = (ket_eff + TILE_KET - 1) / TILE_KET;
+      // one CTA per (bra tile row, ket tile); the kernel's tile loop (ysplit < nbx) is kept for experiments only
+      const int ysplit = prm.nbx;
+      prm.ysplit = ysplit;
+      const int64_t grid = (int64_t)nrows_local * ysplit;
       prm.counters = b->d_counters + 2 * qc;
       if (prof && !qc_started[qc]) cudaEventRecord(b->ev[4 + 2 * qc], s);
       qc_started[qc] = true;
@@ -582,34 +570,9 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
         }
         ls = e.side_stream;
       }
-      // screening pass -> compact list -> list-driven class kernel, in batches of bra tile rows that fit the list buffer
-      const int64_t per_row = (int64_t)TILE_BRA * prm.nbx * TILE_KET;  // candidates per tile row (upper bound on survivors)
-      int rows_per_batch = (int)std::max<int64_t>(1, std::min<int64_t>(nrows_local, (int64_t)b->list_cap / per_row));
-      for (int r0 = 0; r0 < nrows_local; r0 += rows_per_batch) {
-        const int nr = std::min(rows_per_batch, nrows_local - r0);
-        if (list_slot >= LIST_SLOTS) {
-          set_error("qlb_build_jk_device: too many screening launches in one build");
-          return QLB_ERR_ARG;
-        }
-        prm.row0 = r0 * nranks;
-        prm.list = b->d_list;
-        prm.list_cap = (unsigned)std::min<size_t>(b->list_cap, 0xffffffffu);
-        prm.list_count = b->d_list_counts + list_slot++;
-        slot_qc.push_back(qc);
-        const int64_t grid = (int64_t)nr * prm.nbx;
-        if (grid > 0x7fffffffLL || per_row > (int64_t)b->list_cap) {
-          set_error("qlb_build_jk_device: screening grid / list buffer too small for this class");
-          return QLB_ERR_ARG;
-        }
-        screen_kernel<<<(unsigned)grid, dim3(TILE_KET, TILE_BRA), 0, ls>>>(prm);
-        QLB_CUDA(cudaGetLastError());
-        ++launches;
-        // grid-stride consumers: enough CTAs to fill the machine, never more than the candidates could need
-        const unsigned cgrid = (unsigned)std::min<int64_t>((int64_t)e.sm_count * 16, (grid * TILE_KET * TILE_BRA + 127) / 128);
-        if (int ce = launch_class_kernel(X, Y, 0, cgrid, ls, prm)) return cuda_fail((cudaError_t)ce, "eri_list_kernel");
-        launches += launch_count_of(X, Y);
-      }
+      if (int ce = launch_class_kernel(X, Y, 0, (unsigned)grid, ls, prm)) return cuda_fail((cudaError_t)ce, "eri_class_kernel");
       if (prof) cudaEventRecord(b->ev[4 + 2 * qc + 1], s);
+      launches += launch_count_of(X, Y);
     }
   if (forked) {
     QLB_CUDA(cudaEventRecord(e.ev_join, e.side_stream));
@@ -618,17 +581,8 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
   if (stats) {
     cudaEventRecord(b->ev[2], s);
     unsigned long long h[2 * NQCLASS];
-    std::vector<unsigned> hl(std::max(list_slot, 1));
     QLB_CUDA(cudaMemcpyAsync(h, b->d_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
-    QLB_CUDA(cudaMemcpyAsync(hl.data(), b->d_list_counts, hl.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     QLB_CUDA(cudaStreamSynchronize(s));
-    for (int i = 0; i < list_slot; ++i) {
-      if (hl[i] > b->list_cap) {
-        set_error("qlb_build_jk_device: quartet list overflow (internal error)");
-        return QLB_ERR_STATE;
-      }
-      h[2 * slot_qc[i]] += hl[i];  // the list length is the exact number of surviving quartets
-    }
     memset(stats, 0, sizeof(*stats));
     stats->quartets_unique = b->npairs * (b->npairs + 1) / 2;
     stats->pairs_total = b->npairs;
@@ -742,6 +696,7 @@ static int tensor_device(qlb_basis *b, double *dT) {
       if (prm.bra_n == 0 || prm.ket_n == 0) continue;
       prm.same = (X == Y) ? 1 : 0;
       prm.nbx = (prm.ket_n + TILE_KET - 1) / TILE_KET;
+      prm.ysplit = prm.nbx;
       const int64_t grid = (int64_t)((prm.bra_n + TILE_BRA - 1) / TILE_BRA) * prm.nbx;
       if (int ce = launch_class_kernel(X, Y, 1, (unsigned)grid, e.stream, prm)) return cuda_fail((cudaError_t)ce, "eri_class_kernel(tensor)");
     }

@@ -22,10 +22,11 @@ namespace qlb {
 #ifdef QC_DSEL
 // ---- one ket-d component of a split class
 int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, QC_DSEL)(unsigned grid, cudaStream_t s, const ClassParams &prm) {
+  const dim3 block(TILE_KET, TILE_BRA);
 #if QC_UNR
-  unr::eri_list_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, QC_DSEL, QC_MINB><<<grid, 128, 0, s>>>(prm);
+  unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, 1, QC_DSEL, QC_MINB><<<grid, block, 0, s>>>(prm);
 #else
-  rol::eri_list_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, QC_DSEL, QC_MINB><<<grid, 128, 0, s>>>(prm);
+  rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, 1, QC_DSEL, QC_MINB><<<grid, block, 0, s>>>(prm);
 #endif
   return (int)cudaGetLastError();
 }
@@ -55,9 +56,9 @@ int QC_CAT(QC_LA, QC_LB, QC_LC, QC_LD)(int mode, unsigned grid, cudaStream_t s, 
 #endif
     return rc;
 #elif QC_UNR
-    unr::eri_list_kernel<QC_LA, QC_LB, QC_LC, QC_LD, QC_DSTEP, -1, QC_MINB><<<grid, 128, 0, s>>>(prm);
+    unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, QC_DSTEP, -1, QC_MINB><<<grid, block, 0, s>>>(prm);
 #else
-    rol::eri_list_kernel<QC_LA, QC_LB, QC_LC, QC_LD, QC_DSTEP, -1, QC_MINB><<<grid, 128, 0, s>>>(prm);
+    rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, QC_DSTEP, -1, QC_MINB><<<grid, block, 0, s>>>(prm);
 #endif
   } else {
     rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, ncart(QC_LD)><<<grid, block, 0, s>>>(prm);

@@ -67,16 +67,12 @@ struct ClassParams {
   int tlog, dlmax, screen;
   // sharding of bra tile rows over ranks, grid decoding
   int rank, nranks, nbx;
+  int ysplit;                          // CTAs per bra tile row; CTA y handles ket tiles y, y+ysplit, ...
   // data
   const double *__restrict__ P;
   double *J, *K;
   double *tensor;                      // MODE 1: N^4 output
   unsigned long long *counters;        // [0] quartets kept, [1] primitive quartets
-  // compact list of surviving quartets (screen_kernel -> eri_list_kernel)
-  int2 *list;                          // (bra index, ket index) within the launch's segments
-  unsigned *list_count;                // entries written
-  unsigned list_cap;
-  int row0;                            // first bra tile row of this batch
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -85,57 +81,12 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-struct ClassParams;
-__global__ void screen_kernel(const __grid_constant__ ClassParams prm);
-
 struct QuartetCtx {
   bool active;
   double deg;
   int fa, fb, fc, fd;  // first basis function of each shell
-  int bra_key;         // lanes with equal keys share the bra pair (J_ab is reduced per group)
 };
 
-}  // namespace qlb
-
-namespace qlb {
-// K3: screening pass.  Same tile geometry as the tile kernel (4 bra pairs x 32 ket pairs per CTA); every thread applies
-// the integer Schwarz x density rule to one candidate quartet and the survivors are appended, warp-aggregated, to a
-// compact list in HBM (8 B per quartet) that eri_list_kernel consumes.  Bit-exact counts: the list length IS the count.
-#ifdef QLB_DEFINE_SCREEN_KERNEL
-__global__ void __launch_bounds__(TILE_KET *TILE_BRA) screen_kernel(const __grid_constant__ ClassParams prm) {
-  const int row = prm.row0 + (blockIdx.x / prm.nbx) * prm.nranks + prm.rank;
-  const int bx = blockIdx.x % prm.nbx;
-  const int ib0 = row * TILE_BRA, ik0 = bx * TILE_KET;
-  if (ib0 >= prm.bra_n) return;
-  if (prm.same && ik0 > ib0 + TILE_BRA - 1) return;
-  if (prm.screen && prm.pair_ql[prm.bra_off + ib0] + prm.pair_ql[prm.ket_off + ik0] + prm.dlmax < prm.tlog) return;
-  const int ib = ib0 + threadIdx.y, ik = ik0 + threadIdx.x;
-  bool active = ib < prm.bra_n && ik < prm.ket_n && (!prm.same || ik <= ib);
-  if (prm.screen && active) {
-    const int gb = prm.bra_off + ib, gk = prm.ket_off + ik;
-    const int s = prm.pair_ql[gb] + prm.pair_ql[gk];
-    if (s + prm.dlmax < prm.tlog) active = false;
-    else {
-      const int sa = prm.pair_a[gb], sb = prm.pair_b[gb], sc = prm.pair_a[gk], sd = prm.pair_b[gk];
-      const int *__restrict__ dl = prm.dl;
-      const int n = prm.nsh;
-      int dm = max(dl[sa + n * sb], dl[sc + n * sd]);
-      dm = max(dm, max(dl[sa + n * sc], dl[sa + n * sd]));
-      dm = max(dm, max(dl[sb + n * sc], dl[sb + n * sd]));
-      active = (s + dm >= prm.tlog);
-    }
-  }
-  const unsigned m = __ballot_sync(0xffffffffu, active);
-  if (m == 0u) return;
-  unsigned base = 0;
-  if (threadIdx.x == 0) base = atomicAdd(prm.list_count, (unsigned)__popc(m));
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (active) {
-    const unsigned pos = base + __popc(m & ((1u << threadIdx.x) - 1u));
-    if (pos < prm.list_cap) prm.list[pos] = make_int2(ib, ik);
-  }
-}
-#endif
 }  // namespace qlb
 
 // The ERI / digestion templates are compiled twice from the same source: namespace `unr` with every loop fully
@@ -180,7 +131,7 @@ __global__ void __launch_bounds__(64) schwarz_kernel(const __grid_constant__ Sch
   pr.Bx = prm.sh_xyz[3 * sb]; pr.By = prm.sh_xyz[3 * sb + 1]; pr.Bz = prm.sh_xyz[3 * sb + 2];
   double acc[NA * NB * NA * NB];
   for (int k = 0; k < NA * NB * NA * NB; ++k) acc[k] = 0.0;
-  rol::quartet_accumulate<LA, LB, LA, LB, 0, NB>(prm.pp, pr, pr, prm.boys, acc);
+  rol::quartet_accumulate<LA, LB, LA, LB, 0, NB>(prm.pp, pr, pr, prm.boys + (size_t)(2 * (LA + LB)) * BOYS_TABLE_DOUBLES, acc);
   double m = 0.0;
   int ib = 0;
   for (int bx = LB; bx >= 0; --bx)

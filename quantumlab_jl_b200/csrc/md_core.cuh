@@ -25,31 +25,38 @@ __host__ __device__ constexpr int hidx(int L, int t, int u, int v) {
 }
 
 // ------------------------------------------------------------------ Boys function
-// Table: rows T_i = i*BOYS_DT (i = 0..BOYS_NROW-1), columns m = 0..BOYS_NCOL-1 holding F_m(T_i).
-// F_L(T) by an 8-term Taylor expansion about the nearest row, lower orders by downward recursion;
-// beyond the table by the asymptotic F_0 and upward recursion (exp(-T) kept).  Accurate to ~1e-15 relative.
-constexpr int BOYS_NCOL = 24;           // columns 0..22: F_m(T_i) (total L <= 15); column 23: exp(-T_i)
-constexpr int BOYS_EXPCOL = BOYS_NCOL - 1;
+// One table per total angular momentum L (a class kernel needs exactly one): rows T_i = i*BOYS_DT, each row
+// {F_L(T_i) .. F_{L+7}(T_i), exp(-T_i), pad} = 80 B, read as 16-byte vectors.  29 KB per L: the class kernels keep
+// their table in shared memory (ncu: with the table in global memory the low classes were bound by L1 wavefronts,
+// every lane touching its own row).  F_L(T) by an 8-term Taylor expansion about the nearest row, lower orders by
+// downward recursion with exp(-T) = exp(-T_i) * poly(T_i - T); beyond the table the asymptotic F_0 and upward
+// recursion.  Accurate to ~1e-15 relative.
+constexpr int BOYS_ROWLEN = 10;
+constexpr int BOYS_LMAX = 8;            // (dd|dd)
 constexpr double BOYS_DT = 0.1;
 constexpr double BOYS_TMAX = 36.0;
 constexpr int BOYS_NROW = 362;          // rows 0..361 (T up to 36.1)
+constexpr int BOYS_TABLE_DOUBLES = BOYS_NROW * BOYS_ROWLEN;
 
+// tab: the table of THIS L (global or shared memory)
 template <int L>
-__device__ __forceinline__ void boys_array(double T, const double *__restrict__ tab, double *F) {
+__device__ __forceinline__ void boys_array(double T, const double *tab, double *F) {
   if (T < BOYS_TMAX) {
     const int i = (int)(T * (1.0 / BOYS_DT) + 0.5);
     const double d = (double)i * BOYS_DT - T;  // T_i - T, |d| <= DT/2
-    const double *row = tab + i * BOYS_NCOL;
-    double f = __ldg(row + L + 7);
-#pragma unroll
-    for (int k = 6; k >= 0; --k) f = fma(f, d * (1.0 / (k + 1)), __ldg(row + L + k));
+    const double2 *row = reinterpret_cast<const double2 *>(tab + i * BOYS_ROWLEN);
+    const double2 r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2), r3 = __ldg(row + 3);
+    double f = r3.y;
+    f = fma(f, d * (1.0 / 7), r3.x); f = fma(f, d * (1.0 / 6), r2.y); f = fma(f, d * (1.0 / 5), r2.x);
+    f = fma(f, d * (1.0 / 4), r1.y); f = fma(f, d * (1.0 / 3), r1.x); f = fma(f, d * (1.0 / 2), r0.y);
+    f = fma(f, d, r0.x);
     F[L] = f;
     if (L > 0) {
-      // exp(-T) = exp(-T_i) * exp(d): tabulated exp(-T_i) (last column) times a degree-8 Taylor polynomial (|d|<=0.05)
+      // exp(-T) = exp(-T_i) * exp(d): tabulated exp(-T_i) times a degree-8 Taylor polynomial (|d| <= 0.05)
       double e = 1.0 / 40320.0;
       e = fma(e, d, 1.0 / 5040.0); e = fma(e, d, 1.0 / 720.0); e = fma(e, d, 1.0 / 120.0); e = fma(e, d, 1.0 / 24.0);
       e = fma(e, d, 1.0 / 6.0); e = fma(e, d, 0.5); e = fma(e, d, 1.0); e = fma(e, d, 1.0);
-      e *= __ldg(row + BOYS_EXPCOL);
+      e *= __ldg(row + 4).x;
       const double t2 = 2.0 * T;
 #pragma unroll
       for (int m = L; m >= 1; --m) F[m - 1] = fma(t2, F[m], e) * (1.0 / (2 * m - 1));

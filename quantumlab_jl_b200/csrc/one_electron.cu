@@ -17,7 +17,7 @@ __device__ static void boys_rt(int L, double T, const double *__restrict__ tab, 
   if (T < BOYS_TMAX) {
     const int i = (int)(T * (1.0 / BOYS_DT) + 0.5);
     const double d = (double)i * BOYS_DT - T;
-    const double *row = tab + i * BOYS_NCOL + L;
+    const double *row = tab + (size_t)L * BOYS_TABLE_DOUBLES + i * BOYS_ROWLEN;
     double f = row[7];
     for (int k = 6; k >= 0; --k) f = fma(f, d / (k + 1), row[k]);
     F[L] = f;

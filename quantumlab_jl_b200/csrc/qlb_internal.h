@@ -70,9 +70,6 @@ struct qlb_basis {
   double *d_P = nullptr, *d_JK = nullptr, *d_H = nullptr;  // N*N, 2*N*N, N*N
   int *d_dl = nullptr;                                      // nsh*nsh (+1 slot for the max)
   unsigned long long *d_counters = nullptr;                 // 2 per quartet class
-  int2 *d_list = nullptr;                                   // compact quartet list (screen_kernel -> eri_list_kernel)
-  size_t list_cap = 0;
-  unsigned *d_list_counts = nullptr;                        // one counter per screening launch of a build
   cudaEvent_t ev[2 * qlb::NQCLASS + 4] = {nullptr};
 };
 
