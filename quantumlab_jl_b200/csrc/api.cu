@@ -186,9 +186,11 @@ extern "C" int qlb_init(int device) {
   e.device = device;
   e.sm_count = prop.multiProcessorCount;
   QLB_CUDA(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
-  QLB_CUDA(cudaStreamCreateWithFlags(&e.side_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < Engine::NSIDE; ++i) {
+    QLB_CUDA(cudaStreamCreateWithFlags(&e.side_stream[i], cudaStreamNonBlocking));
+    QLB_CUDA(cudaEventCreateWithFlags(&e.ev_join[i], cudaEventDisableTiming));
+  }
   QLB_CUDA(cudaEventCreateWithFlags(&e.ev_fork, cudaEventDisableTiming));
-  QLB_CUDA(cudaEventCreateWithFlags(&e.ev_join, cudaEventDisableTiming));
   std::vector<double> tab;
   make_boys_table(tab);
   QLB_CUDA(cudaMalloc((void **)&e.d_boys, tab.size() * sizeof(double)));
@@ -206,9 +208,11 @@ extern "C" int qlb_finalize(void) {
   cudaSetDevice(e.device);
   if (e.d_boys) cudaFree(e.d_boys);
   if (e.stream) cudaStreamDestroy(e.stream);
-  if (e.side_stream) cudaStreamDestroy(e.side_stream);
+  for (int i = 0; i < Engine::NSIDE; ++i) {
+    if (e.side_stream[i]) cudaStreamDestroy(e.side_stream[i]);
+    if (e.ev_join[i]) cudaEventDestroy(e.ev_join[i]);
+  }
   if (e.ev_fork) cudaEventDestroy(e.ev_fork);
-  if (e.ev_join) cudaEventDestroy(e.ev_join);
   e = Engine();
   return QLB_OK;
 }
@@ -529,6 +533,7 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
   if (stats) cudaEventRecord(b->ev[1], s);
   bool qc_started[NQCLASS] = {false};
   bool forked = false;
+  int nlaunch_classes = 0;
   // heaviest classes first; within a class pair, every (bra segment, ket segment) combination is one launch
   int cls_seg[NCLASS + 1];  // segment range of each class
   for (int c = 0, sg = 0; c <= NCLASS; ++c) {
@@ -559,25 +564,26 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       prm.counters = b->d_counters + 2 * qc;
       if (prof && !qc_started[qc]) cudaEventRecord(b->ev[4 + 2 * qc], s);
       qc_started[qc] = true;
-      // (dd|dd) has few quartets, each with a long serial body: it cannot fill the GPU, so it runs on a side stream
-      // concurrently with the rest of the classes (all classes only add into J/K with atomics)
+      // deal the class launches over the build stream and the side streams (not while timing classes individually)
       cudaStream_t ls = s;
-      if (!prof && X == NCLASS - 1 && Y == NCLASS - 1) {
+      if (!prof) {
         if (!forked) {
           QLB_CUDA(cudaEventRecord(e.ev_fork, s));
-          QLB_CUDA(cudaStreamWaitEvent(e.side_stream, e.ev_fork, 0));
+          for (int i = 0; i < Engine::NSIDE; ++i) QLB_CUDA(cudaStreamWaitEvent(e.side_stream[i], e.ev_fork, 0));
           forked = true;
         }
-        ls = e.side_stream;
+        const int which = nlaunch_classes++ % (Engine::NSIDE + 1);
+        if (which > 0) ls = e.side_stream[which - 1];
       }
       if (int ce = launch_class_kernel(X, Y, 0, (unsigned)grid, ls, prm)) return cuda_fail((cudaError_t)ce, "eri_class_kernel");
       if (prof) cudaEventRecord(b->ev[4 + 2 * qc + 1], s);
       launches += launch_count_of(X, Y);
     }
-  if (forked) {
-    QLB_CUDA(cudaEventRecord(e.ev_join, e.side_stream));
-    QLB_CUDA(cudaStreamWaitEvent(s, e.ev_join, 0));
-  }
+  if (forked)
+    for (int i = 0; i < Engine::NSIDE; ++i) {
+      QLB_CUDA(cudaEventRecord(e.ev_join[i], e.side_stream[i]));
+      QLB_CUDA(cudaStreamWaitEvent(s, e.ev_join[i], 0));
+    }
   if (stats) {
     cudaEventRecord(b->ev[2], s);
     unsigned long long h[2 * NQCLASS];

@@ -26,8 +26,11 @@ struct Engine {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t side_stream = nullptr;  // sparsely populated classes run beside the main sequence
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // class kernels are independent (they only add into J/K): they are dealt over the build stream plus these side
+  // streams so that the tail of one class overlaps the body of the next
+  static constexpr int NSIDE = 3;
+  cudaStream_t side_stream[NSIDE] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {nullptr, nullptr, nullptr};
   double *d_boys = nullptr;
   bool profiling = false;
   // NCCL (loaded lazily with dlopen)
