@@ -288,12 +288,12 @@ def run_ours(args):
         shard_err = float(np.abs(dF.cpu().numpy().reshape(N, N) - F_dev).max())
 
     # ---- timed region 1: device resident
+    sampler = ClockSampler(local)
+    sampler.start()  # before the warm-up: nvidia-smi's start-up must not land inside the timed region
     for _ in range(args.warmup):
         flush.zero_()
         step_device()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b_ in ev:
         flush.zero_()  # L2 flush between steps (outside the step's event pair)

@@ -553,8 +553,11 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       if (screen) ket_eff = std::min(ket_eff, prefix_count(b, sy, tlog - dlmax - b->h_pair_ql[b->seg_off[sx]]));
       if (ket_eff == 0) continue;
       if (prm.same) ket_eff = std::min(ket_eff, prm.bra_n);
+      // tile rows are dealt round-robin; the rank that receives row 0 (the heaviest) rotates with the class pair
+      const int vrank = (rank + qc) % nranks;
+      prm.rank = vrank;
       const int nrows = (prm.bra_n + TILE_BRA - 1) / TILE_BRA;
-      const int nrows_local = rank < nrows ? (nrows - rank + nranks - 1) / nranks : 0;
+      const int nrows_local = vrank < nrows ? (nrows - vrank + nranks - 1) / nranks : 0;
       if (nrows_local == 0) continue;
       prm.nbx = (ket_eff + TILE_KET - 1) / TILE_KET;
       // one CTA per (bra tile row, ket tile); the kernel's tile loop (ysplit < nbx) is kept for experiments only

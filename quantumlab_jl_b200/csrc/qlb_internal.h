@@ -28,9 +28,9 @@ struct Engine {
   cudaStream_t stream = nullptr;
   // class kernels are independent (they only add into J/K): they are dealt over the build stream plus these side
   // streams so that the tail of one class overlaps the body of the next
-  static constexpr int NSIDE = 3;
-  cudaStream_t side_stream[NSIDE] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {nullptr, nullptr, nullptr};
+  static constexpr int NSIDE = 7;
+  cudaStream_t side_stream[NSIDE] = {nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {nullptr};
   double *d_boys = nullptr;
   bool profiling = false;
   // NCCL (loaded lazily with dlopen)
