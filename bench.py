@@ -97,6 +97,7 @@ def cpu_reference_sample(shells, P, budget_s, nthreads):
 def cpu_fair_sample(shells, P, tau, budget_s):
     """Same algorithm family as the GPU path (MD, 8-fold symmetry, same screening), OpenMP over all host cores."""
     orc, b = oracle_basis(shells)
+    orc.set_num_threads(os.cpu_count() or 1)  # torch / torchrun may have pinned OpenMP to one thread
     Q = orc.schwarz(b)
     npair = b.nsh * (b.nsh + 1) // 2
     nranks = max(1, npair // 400)

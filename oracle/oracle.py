@@ -160,6 +160,10 @@ def qlog(x: float) -> int:
     return lib().orc_qlog(x)
 
 
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(C.c_int(int(n)))
+
+
 def num_threads() -> int:
     return lib().orc_num_threads()
 

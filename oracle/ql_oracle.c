@@ -896,6 +896,12 @@ void orc_screen_count(int nsh, const int *L, const double *Q, const double *P, d
   free(ql); free(dl); free(boff);
 }
 
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
