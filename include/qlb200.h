@@ -127,6 +127,23 @@ int qlb_overlap(qlb_basis *b, double *S);
 int qlb_kinetic(qlb_basis *b, double *T);
 int qlb_nuclear_attraction(qlb_basis *b, int natoms, const double *xyz, const double *Z, double *V);
 
+/* ---- resolution of the identity, Coulomb metric (ResolutionIdentityModule.jl:41-78) -------------------------
+ * qlb_ri_create   builds B = (mu nu|P)(P|Q)^-1/2 on the device for an auxiliary shell list (same array conventions as
+ *                 qlb_basis_create): replaces computeMatrixResolutionOfTheIdentityCoulombMetric (:41-50).
+ * qlb_ri_b_tensor copies B out as the reference's N x N x Naux array.
+ * qlb_ri_build_jk J[mu,nu] = sum_Q B[mu,nu,Q] sum B[la,si,Q] P[la,si]  (RI-J; new) and
+ *                 K[mu,la] = sum_Q sum B[mu,nu,Q] P[nu,si] B[la,si,Q]  = computeMatrixExchangeRIK (:69-78), as dense
+ *                 FP64 GEMMs (cuBLAS, DMMA); the N^4 tensor of the reference is never formed.  ms (optional): device
+ *                 time of the contractions. */
+typedef struct qlb_ri qlb_ri;
+int qlb_ri_create(qlb_basis *orbital, int naux_sh, const double *centers, const int32_t *L, const int32_t *nprim,
+                  const double *exps, const double *coefs, qlb_ri **out);
+int qlb_ri_destroy(qlb_ri *r);
+int qlb_ri_naux(const qlb_ri *r, int *naux);
+int qlb_ri_b_tensor(qlb_ri *r, double *B);
+int qlb_ri_eri_tensor(qlb_ri *r, double *out); /* B B^T as N^4 (computeTensorElectronRepulsionIntegralsRICoulomb :54-58), N <= 64 */
+int qlb_ri_build_jk(qlb_ri *r, const double *P, double *J, double *K, double *ms);
+
 /* ---- knobs ---------------------------------------------------------------------------------------------- */
 int qlb_set_profiling(int on); /* time every class kernel with its own event pair (serialises the classes) */
 int qlb_fp64_peak_probe(double *tflops); /* DFMA microbenchmark: the measured FP64 roofline denominator */

@@ -156,6 +156,41 @@ def screen_count(b: Basis, Q, P, tau=1e-12):
     return counts[0], counts[1]
 
 
+def ri_b_tensor(b_orb: Basis, b_aux: Basis):
+    """ResolutionIdentityModule.jl:41-50: B[mu,nu,P] = (mu nu|P 1)(P 1|Q 1)^-1/2 with the unit s function
+    (exponent 0, coefficient 1, at the origin) standing in for identityCGF (BasisFunctionsModule.jl:50-51)."""
+    centers = np.concatenate([b_orb.centers, b_aux.centers, np.zeros(3)])
+    L = np.concatenate([b_orb.L, b_aux.L, [0]]).astype(np.int32)
+    nprim = np.concatenate([b_orb.nprim, b_aux.nprim, [1]]).astype(np.int32)
+    exps = np.concatenate([b_orb.exps, b_aux.exps, [0.0]])
+    coefs = np.concatenate([b_orb.coefs, b_aux.coefs, [1.0]])
+    comb = Basis(centers, L, nprim, exps, coefs)
+    N, Nx = b_orb.N, b_aux.N
+    unit = comb.nsh - 1
+    B3 = np.zeros((N, N, Nx))
+    for i in range(b_orb.nsh):
+        for j in range(b_orb.nsh):
+            for k in range(b_aux.nsh):
+                blk = eri_block(comb, i, j, b_orb.nsh + k, unit, literal=False)
+                B3[b_orb.boff[i]:b_orb.boff[i + 1], b_orb.boff[j]:b_orb.boff[j + 1], b_aux.boff[k]:b_aux.boff[k + 1]] = blk[:, :, :, 0]
+    M = np.zeros((Nx, Nx))
+    for k in range(b_aux.nsh):
+        for l in range(b_aux.nsh):
+            blk = eri_block(comb, b_orb.nsh + k, unit, b_orb.nsh + l, unit, literal=False)
+            M[b_aux.boff[k]:b_aux.boff[k + 1], b_aux.boff[l]:b_aux.boff[l + 1]] = blk[:, 0, :, 0]
+    w, v = np.linalg.eigh(0.5 * (M + M.T))
+    Mih = (v * w ** -0.5) @ v.T  # sqrt(inv(C))
+    return (B3.reshape(N * N, Nx, order="F") @ Mih).reshape((N, N, Nx), order="F")
+
+
+def ri_exchange(B, P):  # ResolutionIdentityModule.jl:69-78
+    return np.einsum("mnq,ns,lsq->ml", B, P, B, optimize=True)
+
+
+def ri_coulomb(B, P):
+    return np.einsum("mnq,q->mn", B, np.einsum("lsq,ls->q", B, P))
+
+
 def qlog(x: float) -> int:
     return lib().orc_qlog(x)
 

@@ -286,14 +286,21 @@ static int basis_build_pairs(qlb_basis *b) {
   Engine &e = g_engine;
   const int nsh = b->nsh;
   // enumerate unique pairs, canonical orientation la >= lb, bucketed by class in (i,j) order
-  std::vector<int> pa[NCLASS], pb[NCLASS];
-  for (int i = 0; i < nsh; ++i)
+  std::vector<int> pa[2 * NCLASS], pb[2 * NCLASS];
+  const int nreg = b->n_orb > 0 ? b->n_orb : nsh;
+  for (int i = 0; i < nreg; ++i)
     for (int j = 0; j <= i; ++j) {
       int a = i, c = j;
       if (b->h_L[a] < b->h_L[c]) std::swap(a, c);
       const int cls = class_of(b->h_L[a], b->h_L[c]);
       pa[cls].push_back(a);
       pb[cls].push_back(c);
+    }
+  if (b->n_orb > 0)  // RI: (auxiliary shell, unit s function) pairs form the second group
+    for (int k = b->n_orb; k < nsh - 1; ++k) {
+      const int cls = NCLASS + class_of(b->h_L[k], 0);
+      pa[cls].push_back(k);
+      pb[cls].push_back(nsh - 1);
     }
   b->h_pair_a.clear();
   b->h_pair_b.clear();
@@ -302,6 +309,12 @@ static int basis_build_pairs(qlb_basis *b) {
     b->h_pair_a.insert(b->h_pair_a.end(), pa[c].begin(), pa[c].end());
     b->h_pair_b.insert(b->h_pair_b.end(), pb[c].begin(), pb[c].end());
     b->class_off[c + 1] = (int)b->h_pair_a.size();
+  }
+  b->ri_class_off[0] = (int)b->h_pair_a.size();
+  for (int c = 0; c < NCLASS; ++c) {
+    b->h_pair_a.insert(b->h_pair_a.end(), pa[NCLASS + c].begin(), pa[NCLASS + c].end());
+    b->h_pair_b.insert(b->h_pair_b.end(), pb[NCLASS + c].begin(), pb[NCLASS + c].end());
+    b->ri_class_off[c + 1] = (int)b->h_pair_a.size();
   }
   b->npairs = (int64_t)b->h_pair_a.size();
   compute_pair_offsets(b);
@@ -316,7 +329,8 @@ static int basis_build_pairs(qlb_basis *b) {
   QLB_CUDA(cudaMalloc((void **)&b->d_pair_Q, std::max<int64_t>(b->npairs, 1) * sizeof(double)));
   QLB_CUDA(cudaMalloc((void **)&b->d_pair_ql, std::max<int64_t>(b->npairs, 1) * sizeof(int)));
   if (int rc = run_pair_prims(b)) return rc;
-  // K2: Schwarz bounds per pair
+  // K2: Schwarz bounds per pair (the (aux, unit) pairs of an RI basis keep bound 0: they are never screened)
+  QLB_CUDA(cudaMemsetAsync(b->d_pair_Q, 0, std::max<int64_t>(b->npairs, 1) * sizeof(double), e.stream));
   SchwarzParams sp;
   sp.sh_xyz = b->d_xyz; sp.pair_a = b->d_pair_a; sp.pair_b = b->d_pair_b; sp.pair_poff = b->d_pair_poff;
   fill_pp(b, sp.pp);
@@ -351,7 +365,7 @@ static int basis_build_pairs(qlb_basis *b) {
         b->seg_cls.push_back(c);
       }
   }
-  b->seg_off.push_back((int)b->npairs);
+  b->seg_off.push_back(b->class_off[NCLASS]);
   std::vector<int> na(b->npairs), nb(b->npairs);
   std::vector<double> nq(b->npairs);
   b->h_pair_ql.resize(b->npairs);
@@ -379,6 +393,11 @@ static int basis_build_pairs(qlb_basis *b) {
 
 extern "C" int qlb_basis_create(int nsh, const double *centers, const int32_t *L, const int32_t *nprim,
                                 const double *exps, const double *coefs, qlb_basis **out) {
+  return qlb::basis_create_internal(nsh, centers, L, nprim, exps, coefs, 0, out);
+}
+
+int qlb::basis_create_internal(int nsh, const double *centers, const int32_t *L, const int32_t *nprim, const double *exps,
+                               const double *coefs, int n_orb, qlb_basis **out) {
   if (int rc = require_ready()) return rc;
   if (!out || nsh <= 0 || !centers || !L || !nprim || !exps || !coefs) {
     set_error("qlb_basis_create: null pointer or nsh <= 0");
@@ -387,6 +406,7 @@ extern "C" int qlb_basis_create(int nsh, const double *centers, const int32_t *L
   QLB_CUDA(cudaSetDevice(g_engine.device));
   qlb_basis *b = new qlb_basis();
   b->nsh = nsh;
+  b->n_orb = n_orb;
   b->h_xyz.assign(centers, centers + 3 * (size_t)nsh);
   b->h_L.assign(L, L + nsh);
   b->h_nprim.assign(nprim, nprim + nsh);
@@ -460,6 +480,9 @@ extern "C" int qlb_schwarz(qlb_basis *b, double *Q) {
 }
 
 // =================================================================== J/K
+static void base_params(qlb_basis *b, ClassParams &prm);
+void qlb::base_class_params(qlb_basis *b, ClassParams &prm) { base_params(b, prm); }
+
 static void base_params(qlb_basis *b, ClassParams &prm) {
   memset(&prm, 0, sizeof(prm));
   prm.sh_xyz = b->d_xyz; prm.sh_boff = b->d_boff; prm.nsh = b->nsh; prm.nbf = b->nbf;

@@ -60,8 +60,10 @@ int QC_CAT(QC_LA, QC_LB, QC_LC, QC_LD)(int mode, unsigned grid, cudaStream_t s, 
 #else
     rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, QC_DSTEP, -1, QC_MINB><<<grid, block, 0, s>>>(prm);
 #endif
-  } else {
+  } else if (mode == 1) {
     rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, ncart(QC_LD)><<<grid, block, 0, s>>>(prm);
+  } else {
+    rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 2, ncart(QC_LD)><<<grid, block, 0, s>>>(prm);
   }
   return (int)cudaGetLastError();
 }

@@ -71,7 +71,8 @@ struct ClassParams {
   // data
   const double *__restrict__ P;
   double *J, *K;
-  double *tensor;                      // MODE 1: N^4 output
+  double *tensor;                      // MODE 1: N^4 output; MODE 2: B3 (N*N*Naux) or M (Naux*Naux)
+  int ri_mode, ri_n, ri_naux, ri_aux_fn0;  // MODE 2 (see scatter_ri)
   unsigned long long *counters;        // [0] quartets kept, [1] primitive quartets
 };
 

@@ -58,6 +58,10 @@ struct qlb_basis {
   std::vector<int> h_pair_a, h_pair_b, h_pair_poff, h_pair_ql;
   std::vector<double> h_pair_Q;
   int class_off[qlb::NCLASS + 1] = {0};
+  // resolution of the identity: shells [0,n_orb) orbital, [n_orb, nsh-1) auxiliary, shell nsh-1 the unit s function;
+  // pair group 0 = orbital pairs (class_off), group 1 = (aux, unit) pairs (ri_class_off).  n_orb == 0: ordinary basis
+  int n_orb = 0;
+  int ri_class_off[qlb::NCLASS + 1] = {0};
   // segments: each class is split by contraction degree (primitive pairs per shell pair) so that the threads of a
   // warp run primitive loops of similar length; every segment is sorted by Schwarz bound, descending
   std::vector<int> seg_off, seg_cls;
@@ -82,6 +86,10 @@ int launch_class_kernel(int X, int Y, int mode, unsigned grid, cudaStream_t s, c
 int launch_schwarz_kernel(int X, unsigned grid, cudaStream_t s, const SchwarzParams &prm);
 // flops per primitive quartet / digestion flops per contracted quartet for a quartet class
 void class_flops(int X, int Y, double &f_prim, double &f_digest);
+// internal constructor (api.cu): n_orb > 0 builds the two RI pair groups
+int basis_create_internal(int nsh, const double *centers, const int32_t *L, const int32_t *nprim, const double *exps,
+                          const double *coefs, int n_orb, qlb_basis **out);
+void base_class_params(qlb_basis *b, ClassParams &prm);
 // one-electron kernels (one_electron.cu)
 int one_electron_device(qlb_basis *b, int which, int natoms, const double *d_xyzZ, double *d_out, cudaStream_t s);
 }  // namespace qlb
