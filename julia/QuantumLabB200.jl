@@ -14,7 +14,7 @@ import ..SpecialMatricesModule: computeMatrixCoulomb, computeMatrixExchange, com
                                 computeMatrixOverlap, computeMatrixKinetic, computeMatrixNuclearAttraction
 import ..HartreeFockModule: evaluateSCF
 
-export B200Shells, destroy!
+export B200Shells, B200RI, destroy!
 
 const libqlb = Ref{Ptr{Nothing}}(C_NULL)
 
@@ -139,6 +139,33 @@ function computeTensorBlockElectronRepulsionIntegrals(b::B200Shells, i::Int, j::
   check(ccall(dlsym(libqlb[], :qlb_eri_block), Cint, (Ptr{Nothing}, Cint, Cint, Cint, Cint, Ptr{Float64}),
               b.handle, i - 1, j - 1, k - 1, l - 1, blk))
   blk
+end
+
+# ---- resolution of the identity (ResolutionIdentityModule.jl:41-78): B stays on the device inside the handle
+mutable struct B200RI
+  orbital::B200Shells
+  handle::Ptr{Nothing}
+  naux::Int
+end
+function B200RI(b::B200Shells, aux::Vector{Shell})
+  centers = Float64[c for sh in aux for c in (sh.center.x, sh.center.y, sh.center.z)]
+  L = Int32[sh.lqn.exponent for sh in aux]; nprim = Int32[length(sh.exponents) for sh in aux]
+  exps = vcat([sh.exponents for sh in aux]...); coefs = vcat([sh.coefficients for sh in aux]...)
+  h = Ref{Ptr{Nothing}}(C_NULL)
+  check(ccall(dlsym(libqlb[], :qlb_ri_create), Cint,
+              (Ptr{Nothing}, Cint, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Ptr{Nothing}}),
+              b.handle, length(aux), centers, L, nprim, exps, coefs, h))
+  B200RI(b, h[], mapreduce(nbf, +, aux))
+end
+destroy!(r::B200RI) = (ccall(dlsym(libqlb[], :qlb_ri_destroy), Cint, (Ptr{Nothing},), r.handle); r.handle = C_NULL)
+function computeMatrixResolutionOfTheIdentityCoulombMetric(r::B200RI)                                    # :41-50
+  B = Array{Float64,3}(undef, r.orbital.nbf, r.orbital.nbf, r.naux)
+  check(ccall(dlsym(libqlb[], :qlb_ri_b_tensor), Cint, (Ptr{Nothing}, Ptr{Float64}), r.handle, B)); B
+end
+function computeMatrixExchangeRIK(r::B200RI, density::Matrix)                                            # :69-78
+  K = Matrix{Float64}(undef, r.orbital.nbf, r.orbital.nbf)
+  check(ccall(dlsym(libqlb[], :qlb_ri_build_jk), Cint, (Ptr{Nothing}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+              r.handle, Matrix{Float64}(density), C_NULL, K, C_NULL)); K
 end
 
 # evaluateSCF(basis::B200Shells, geometry, guess, nocc): the convenience form (HartreeFockModule.jl:158-208) with the

@@ -80,3 +80,17 @@ def build(name: str):
     geo = cfg["geometry"]()
     shells = computeBasisShells(loadBasisSet(cfg["basis"]), geo)
     return geo, shells, cfg["nocc"]
+
+
+def even_tempered_aux(geo: Geometry):
+    """A synthetic auxiliary basis (the cc-pVDZ-JKFIT data cannot be vendored offline): per atom even-tempered
+    uncontracted s (6), p (4) and d (3) shells -> 36 Cartesian functions per atom."""
+    from .base import LQuantumNumber
+    from .shell import Shell
+
+    shells = []
+    for atom in geo.atoms:
+        for lsym, a0, n in (("S", 0.10, 6), ("P", 0.20, 4), ("D", 0.30, 3)):
+            for k in range(n):
+                shells.append(Shell(atom.position, LQuantumNumber(lsym), [a0 * 3.0 ** k], [1.0]))
+    return shells
