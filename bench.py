@@ -305,8 +305,9 @@ def run_ours(args):
     clocks = sampler.stop()
     step_ms = [a.elapsed_time(b_) for a, b_ in ev]
     ms_local = sum(step_ms)
-    if rank == 0:
-        print("per-step ms:", " ".join(f"{x:.2f}" for x in step_ms), file=sys.stderr)
+    if rank == 0 or os.environ.get("QLB_BENCH_ALL_RANKS"):
+        print(f"[rank {rank}] per-step ms:", " ".join(f"{x:.2f}" for x in step_ms), f"| serial class-kernel sum {stats['ms_eri']:.2f} ms,"
+              f" quartets {stats['quartets_kept']}, alg flops {stats['flops_algorithmic']:.3e}", file=sys.stderr)
     tms = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)

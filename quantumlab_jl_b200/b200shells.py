@@ -35,6 +35,10 @@ class B200Shells(list):
         self.last_stats: dict | None = None
         self._cache_P = None
         self._cache_JK = None
+        self.incremental = False      # density-difference builds inside an SCF loop
+        self.rebuild_every = 8
+        self._since_full = 0
+        self.build_history: list = []  # quartets kept by each build issued through jk_cached
 
     # ---- handle management
     @property
@@ -75,11 +79,24 @@ class B200Shells(list):
         return J, K
 
     def jk_cached(self, P):
-        """J and K for P, computed together once: `coulomb(P)` followed by `exchange(P)` costs one pass."""
+        """J and K for P, computed together once: `coulomb(P)` followed by `exchange(P)` costs one pass.
+
+        With `incremental=True` a new density is handled as J(P) = J(P_prev) + J(P - P_prev): J and K
+        are linear in P and the density DIFFERENCE shrinks as the SCF converges, so the Schwarz x density rule keeps
+        fewer and fewer quartets.  Every `rebuild_every`-th build is a full one, which bounds the accumulated
+        screening error (each build drops contributions below tau)."""
         P = self._check_P(P)
-        if self._cache_P is None or self._cache_P.shape != P.shape or not np.array_equal(self._cache_P, P):
+        if self._cache_P is not None and self._cache_P.shape == P.shape and np.array_equal(self._cache_P, P):
+            return self._cache_JK
+        if self.incremental and self._cache_P is not None and self._since_full < self.rebuild_every and np.any(self._cache_P):
+            dJ, dK = self.build_jk(P - self._cache_P)
+            self._cache_JK = (self._cache_JK[0] + dJ, self._cache_JK[1] + dK)
+            self._since_full += 1
+        else:
             self._cache_JK = self.build_jk(P)
-            self._cache_P = P.copy()
+            self._since_full = 0
+        self._cache_P = P.copy()
+        self.build_history.append(self.last_stats["quartets_kept"] if self.last_stats else None)
         return self._cache_JK
 
     def fock(self, H, P, tau: float | None = None):

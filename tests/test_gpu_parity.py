@@ -201,6 +201,25 @@ def test_scf_energy_dshell_vs_oracle(orc, qlb):
     assert evaluateSCF.last_iterations == itr
 
 
+def test_incremental_fock_builds(orc, qlb):
+    # density-difference builds reach the same SCF energy with far fewer quartets in late iterations
+    from quantumlab_jl_b200.hartreefock import evaluateSCF
+    from quantumlab_jl_b200.initialguess import ZeroGuess
+
+    geo, shells, b, nocc = make_basis(orc, "h2o2_631gs")
+    full = _b200(shells)
+    _, E_full, _ = evaluateSCF(full, geo, ZeroGuess, nocc, info=False)
+    it_full = evaluateSCF.last_iterations
+    inc = _b200(shells)
+    inc.incremental = True
+    _, E_inc, _ = evaluateSCF(inc, geo, ZeroGuess, nocc, info=False)
+    assert evaluateSCF.last_iterations == it_full
+    assert abs(E_inc - E_full) < 1e-8
+    kept_full = [k for k in full.build_history if k]
+    kept_inc = [k for k in inc.build_history if k]
+    assert min(kept_inc) < 0.95 * min(kept_full)  # the converging density difference is screened harder (small, dense system)
+
+
 def test_benzene_ccpvdz_full_build(orc, qlb):
     geo, shells, b, nocc = make_basis(orc, "benzene_ccpvdz")
     assert b.N == 120 and b.nsh == 54
