@@ -583,8 +583,13 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       const int nrows_local = vrank < nrows ? (nrows - vrank + nranks - 1) / nranks : 0;
       if (nrows_local == 0) continue;
       prm.nbx = (ket_eff + TILE_KET - 1) / TILE_KET;
-      // one CTA per (bra tile row, ket tile); the kernel's tile loop (ysplit < nbx) is kept for experiments only
-      const int ysplit = prm.nbx;
+      static const int ys_target = getenv("QLB_YS_TARGET") ? atoi(getenv("QLB_YS_TARGET")) : 256;
+      static const int ys_tiles = getenv("QLB_YS_TILES") ? atoi(getenv("QLB_YS_TILES")) : 8;
+      int ysplit = (int)std::min<int64_t>(prm.nbx, ((int64_t)e.sm_count * ys_target + nrows_local - 1) / nrows_local);
+      const int ys_amort = std::max(1, prm.nbx / ys_tiles);
+      if ((int64_t)nrows_local * ys_amort >= (int64_t)e.sm_count * 64) ysplit = std::min(ysplit, ys_amort);
+      ysplit = std::max(1, ysplit);
+      if (getenv("QLB_YSPLIT_FULL")) ysplit = prm.nbx;
       prm.ysplit = ysplit;
       const int64_t grid = (int64_t)nrows_local * ysplit;
       prm.counters = b->d_counters + 2 * qc;
