@@ -105,6 +105,11 @@ __global__ void fock_kernel(size_t n, const double *__restrict__ H, const double
   if (i < n) F[i] = H[i] + 2.0 * J[i] - K[i];
 }
 
+__global__ void counters_to_double_kernel(int n, const unsigned long long *__restrict__ c, double *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)c[i];
+}
+
 __global__ void dfma_probe_kernel(double *out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
   const double m = 1.0000001, c = 1e-9;
@@ -273,11 +278,13 @@ extern "C" int qlb_basis_destroy(qlb_basis *b) {
   if (g_engine.ready) cudaSetDevice(g_engine.device);
   void *ptrs[] = {b->d_xyz, b->d_exps, b->d_coefs, b->d_poff, b->d_boff, b->d_L, b->d_pair_a, b->d_pair_b,
                   b->d_pair_poff, b->d_pair_ql, b->d_pair_Q, b->d_pp,
-                  b->d_P, b->d_JK, b->d_H, b->d_dl, b->d_counters};
+                  b->d_P, b->d_JK, b->d_H, b->d_dl, b->d_counters, b->d_gcounts};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (auto &ev : b->ev)
     if (ev) cudaEventDestroy(ev);
+  if (b->ev_gcounts) cudaEventDestroy(b->ev_gcounts);
+  if (b->h_gcounts) cudaFreeHost(b->h_gcounts);
   delete b;
   return QLB_OK;
 }
@@ -449,6 +456,12 @@ int qlb::basis_create_internal(int nsh, const double *centers, const int32_t *L,
     return cuda_fail(ce, "cudaMalloc(scratch)");
   }
   for (auto &ev : b->ev) cudaEventCreate(&ev);
+  cudaEventCreateWithFlags(&b->ev_gcounts, cudaEventDisableTiming);
+  if ((ce = cudaMalloc((void **)&b->d_gcounts, 2 * NQCLASS * sizeof(double))) != cudaSuccess ||
+      (ce = cudaMallocHost((void **)&b->h_gcounts, 2 * NQCLASS * sizeof(double))) != cudaSuccess) {
+    qlb_basis_destroy(b);
+    return cuda_fail(ce, "cudaMalloc(gcounts)");
+  }
   if ((rc = basis_build_pairs(b))) {
     qlb_basis_destroy(b);
     return rc;
@@ -491,6 +504,43 @@ static void base_params(qlb_basis *b, ClassParams &prm) {
   prm.boys = g_engine.d_boys;
   prm.dl = b->d_dl;
   prm.nranks = 1;
+}
+
+// Cost model for dealing class pieces to ranks: algorithmic flops of the class (from the all-rank counters of the
+// previous build) divided by the class kernel's measured efficiency (TFLOP/s, round-1 measurements on B200; only the
+// ratios matter).  Every class pair is cut into 1..nranks pieces of about a third of a rank's share and the pieces
+// are assigned longest-first to the least loaded rank.  Pure function of (counts, nranks): identical on all ranks.
+static bool build_schedule(const double *gc, int rank, int nranks, std::vector<std::pair<int, int>> *mine) {
+  static const double eff[NQCLASS] = {3.28, 3.70, 6.38, 6.45, 12.19, 12.66, 5.07, 8.40, 14.16, 9.40, 10.34,
+                                      11.57, 3.67, 9.26, 2.10, 11.90, 6.08, 3.18, 3.28, 2.58, 0.29};
+  double cost[NQCLASS], total = 0.0;
+  for (int X = 0; X < NCLASS; ++X)
+    for (int Y = 0; Y <= X; ++Y) {
+      const int qc = qclass_of(X, Y);
+      double fp, fd;
+      class_flops(X, Y, fp, fd);
+      cost[qc] = (fp * gc[2 * qc + 1] + fd * gc[2 * qc]) / eff[qc];
+      total += cost[qc];
+    }
+  if (!(total > 0.0)) return false;
+  struct Piece { double c; int qc, p, np; };
+  std::vector<Piece> pieces;
+  const double target = total / (3.0 * nranks);
+  for (int qc = 0; qc < NQCLASS; ++qc) {
+    int np = (int)ceil(cost[qc] / target);
+    np = std::max(1, std::min(np, nranks));
+    for (int p = 0; p < np; ++p) pieces.push_back({cost[qc] / np, qc, p, np});
+  }
+  std::stable_sort(pieces.begin(), pieces.end(), [](const Piece &a, const Piece &b) { return a.c > b.c; });
+  std::vector<double> load(nranks, 0.0);
+  for (const Piece &pc : pieces) {
+    int r = 0;
+    for (int k = 1; k < nranks; ++k)
+      if (load[k] < load[r]) r = k;
+    load[r] += pc.c;
+    if (r == rank) mine[pc.qc].push_back({pc.p, pc.np});
+  }
+  return true;
 }
 
 // kernels launched per class-pair launch (split classes launch one kernel per ket-d component)
@@ -555,6 +605,13 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
   prm.P = dP; prm.J = dJ; prm.K = dK;
   if (stats) cudaEventRecord(b->ev[1], s);
   bool qc_started[NQCLASS] = {false};
+  // ---- multi-rank schedule from the previous build's all-rank counters (identical on every rank)
+  std::vector<std::pair<int, int>> my_pieces[NQCLASS];  // per class pair: (piece index, number of pieces)
+  bool scheduled = false;
+  if (nranks > 1 && b->gcounts_pending && b->gcounts_nranks == nranks && !getenv("QLB_NO_SCHEDULE")) {
+    QLB_CUDA(cudaEventSynchronize(b->ev_gcounts));
+    scheduled = build_schedule(b->h_gcounts, rank, nranks, my_pieces);
+  }
   bool forked = false;
   int nlaunch_classes = 0;
   // heaviest classes first; within a class pair, every (bra segment, ket segment) combination is one launch
@@ -576,11 +633,17 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       if (screen) ket_eff = std::min(ket_eff, prefix_count(b, sy, tlog - dlmax - b->h_pair_ql[b->seg_off[sx]]));
       if (ket_eff == 0) continue;
       if (prm.same) ket_eff = std::min(ket_eff, prm.bra_n);
-      // tile rows are dealt round-robin; the rank that receives row 0 (the heaviest) rotates with the class pair
-      const int vrank = (rank + qc) % nranks;
+      // unscheduled: tile rows are dealt round-robin over all ranks (the rank that receives row 0, the heaviest,
+      // rotates with the class pair).  scheduled: this rank owns whole pieces (row subsets p, p+np, ...) of few classes
+      std::vector<std::pair<int, int>> pieces;
+      if (scheduled) pieces = my_pieces[qc];
+      else pieces.push_back({(rank + qc) % nranks, nranks});
+     for (const auto &piece : pieces) {
+      const int vrank = piece.first, vnranks = piece.second;
       prm.rank = vrank;
+      prm.nranks = vnranks;
       const int nrows = (prm.bra_n + TILE_BRA - 1) / TILE_BRA;
-      const int nrows_local = vrank < nrows ? (nrows - vrank + nranks - 1) / nranks : 0;
+      const int nrows_local = vrank < nrows ? (nrows - vrank + vnranks - 1) / vnranks : 0;
       if (nrows_local == 0) continue;
       prm.nbx = (ket_eff + TILE_KET - 1) / TILE_KET;
       static const int ys_target = getenv("QLB_YS_TARGET") ? atoi(getenv("QLB_YS_TARGET")) : 256;
@@ -609,6 +672,7 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       if (int ce = launch_class_kernel(X, Y, 0, (unsigned)grid, ls, prm)) return cuda_fail((cudaError_t)ce, "eri_class_kernel");
       if (prof) cudaEventRecord(b->ev[4 + 2 * qc + 1], s);
       launches += launch_count_of(X, Y);
+     }  // pieces
     }
   if (forked)
     for (int i = 0; i < Engine::NSIDE; ++i) {
@@ -891,6 +955,14 @@ extern "C" int qlb_allreduce_jk_device(qlb_basis *b, double *dJK, void *stream_)
   const size_t n = 2 * (size_t)b->nbf * b->nbf;
   ncclResult_t r = p_AllReduce(dJK, dJK, n, ncclDouble, ncclSum, (ncclComm_t)e.nccl_comm, s);
   if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce");
+  // schedule feedback: the all-rank per-class quartet / primitive-quartet counts of this build (84 doubles)
+  counters_to_double_kernel<<<1, 64, 0, s>>>(2 * NQCLASS, b->d_counters, b->d_gcounts);
+  r = p_AllReduce(b->d_gcounts, b->d_gcounts, 2 * NQCLASS, ncclDouble, ncclSum, (ncclComm_t)e.nccl_comm, s);
+  if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce(counts)");
+  QLB_CUDA(cudaMemcpyAsync(b->h_gcounts, b->d_gcounts, 2 * NQCLASS * sizeof(double), cudaMemcpyDeviceToHost, s));
+  QLB_CUDA(cudaEventRecord(b->ev_gcounts, s));
+  b->gcounts_pending = true;
+  b->gcounts_nranks = e.nranks;
   return QLB_OK;
 }
 

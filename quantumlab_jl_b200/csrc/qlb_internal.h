@@ -78,6 +78,13 @@ struct qlb_basis {
   int *d_dl = nullptr;                                      // nsh*nsh (+1 slot for the max)
   unsigned long long *d_counters = nullptr;                 // 2 per quartet class
   cudaEvent_t ev[2 * qlb::NQCLASS + 4] = {nullptr};
+  // multi-rank schedule feedback: all-rank per-class counters of the previous build (summed with a second, tiny
+  // all-reduce next to the [J;K] one) drive a cost model that deals whole pieces of classes to ranks
+  double *d_gcounts = nullptr;       // 2*NQCLASS doubles
+  double *h_gcounts = nullptr;       // pinned host copy
+  cudaEvent_t ev_gcounts = nullptr;
+  bool gcounts_pending = false;
+  int gcounts_nranks = 0;
 };
 
 namespace qlb {
