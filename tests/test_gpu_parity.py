@@ -245,3 +245,44 @@ def test_bad_arguments_raise(qlb):
     dev.destroy()
     with pytest.raises(qlb.QlbError):
         dev.build_jk(np.zeros((1, 1)))
+
+
+def _basis_from(orc, shells):
+    from quantumlab_jl_b200.shell import flattenShells
+
+    return orc.Basis(*flattenShells(shells))
+
+
+def test_edge_cases_tiny_ragged_and_distant(orc, qlb):
+    from quantumlab_jl_b200.base import LQuantumNumber, Position
+    from quantumlab_jl_b200.shell import Shell
+
+    S, P_, D = LQuantumNumber("S"), LQuantumNumber("P"), LQuantumNumber("D")
+    cases = {
+        "one s shell": [Shell(Position(0, 0, 0), S, [0.8], [1.0])],
+        "one d shell": [Shell(Position(0.1, -0.2, 0.3), D, [1.1, 0.3], [0.6, 0.5])],
+        "ragged contractions": [Shell(Position(0, 0, 0), S, [50.0, 8.0, 2.0, 0.6, 0.2], [0.05, 0.2, 0.4, 0.4, 0.2]),
+                                Shell(Position(0, 0, 1.4), P_, [0.9], [1.0]),
+                                Shell(Position(1.0, 0.5, 0), D, [0.7], [1.0]),
+                                Shell(Position(0, 0, 1.4), S, [0.3, 0.1], [0.7, 0.4])],
+        "two distant atoms": [Shell(Position(0, 0, 0), S, [1.2, 0.3], [0.5, 0.6]), Shell(Position(0, 0, 0), P_, [0.5], [1.0]),
+                              Shell(Position(0, 0, 60.0), S, [1.2, 0.3], [0.5, 0.6]), Shell(Position(0, 0, 60.0), P_, [0.5], [1.0])],
+    }
+    for name, shells in cases.items():
+        b = _basis_from(orc, shells)
+        dev = _b200(shells)
+        P = _rand_sym(b.N, 21, 0.5)
+        for tau in (0.0, 1e-12):
+            J, K = dev.build_jk(P, tau=tau)
+            Jr, Kr, counts = orc.md_jk(b, P, tau=tau if tau > 0 else 1e-300, Q=dev.schwarz())
+            assert np.abs(J - Jr).max() < TOL_INT and np.abs(K - Kr).max() < TOL_INT, name
+            if tau > 0:  # tau = 0 switches screening off on the device; the oracle still drops exact-zero bounds
+                assert dev.last_stats["quartets_kept"] == counts[0], name
+        if name == "two distant atoms":
+            assert dev.last_stats["quartets_kept"] < dev.last_stats["quartets_unique"]  # cross-centre pairs are screened out
+        T = dev.eri_tensor()
+        assert np.abs(T - orc.eri_tensor(b, literal=False)).max() < TOL_INT, name
+        # everything screened: nothing launched, exact zeros
+        J0, K0 = dev.build_jk(P, tau=1e30)
+        assert not J0.any() and not K0.any() and dev.last_stats["quartets_kept"] == 0
+        dev.destroy()
