@@ -61,15 +61,15 @@ __global__ void pair_prim_kernel(int npairs, const int *__restrict__ pair_a, con
   const double Ax = xyz[3 * a], Ay = xyz[3 * a + 1], Az = xyz[3 * a + 2];
   const double Bx = xyz[3 * b], By = xyz[3 * b + 1], Bz = xyz[3 * b + 2];
   const double ab2 = (Ax - Bx) * (Ax - Bx) + (Ay - By) * (Ay - By) + (Az - Bz) * (Az - Bz);
-  const int base = pair_poff[w];
+  const size_t base = (size_t)pair_poff[w];  // tile layout: primitive t, field f at base + (3 t + f) * 32
   for (int t = lane; t < na * nb; t += 32) {
     const int ia = t / nb, ib = t - ia * nb;
     const double al = exps[oa + ia], be = exps[ob + ib];
     const double p = al + be, ip = 1.0 / p;
-    double2 *r = rec + 3 * (size_t)(base + t);
+    double2 *r = rec + base + (size_t)(3 * TILE_KET) * t;
     r[0] = make_double2(p, (al * Ax + be * Bx) * ip);
-    r[1] = make_double2((al * Ay + be * By) * ip, (al * Az + be * Bz) * ip);
-    r[2] = make_double2(coefs[oa + ia] * coefs[ob + ib] * exp(-al * be * ip * ab2) * ip, 0.5 * ip);
+    r[TILE_KET] = make_double2((al * Ay + be * By) * ip, (al * Az + be * Bz) * ip);
+    r[2 * TILE_KET] = make_double2(coefs[oa + ia] * coefs[ob + ib] * exp(-al * be * ip * ab2) * ip, 0.5 * ip);
   }
 }
 
@@ -150,15 +150,26 @@ static int run_pair_prims(qlb_basis *b) {
   return QLB_OK;
 }
 
+// Tile layout of the primitive-pair records: within each class (and RI group) the pairs are cut into tiles of 32
+// consecutive pairs (= the 32 ket lanes of a warp); a tile with Kmax primitive pairs in its longest pair owns
+// 3*32*Kmax double2 slots, ordered [primitive][field][lane].  h_pair_poff[i] = double2 index of (primitive 0, field 0).
 static void compute_pair_offsets(qlb_basis *b) {
-  b->h_pair_poff.resize(b->npairs + 1);
-  int64_t off = 0;
-  for (int64_t i = 0; i < b->npairs; ++i) {
-    b->h_pair_poff[i] = (int)off;
-    off += (int64_t)b->h_nprim[b->h_pair_a[i]] * b->h_nprim[b->h_pair_b[i]];
-  }
-  b->h_pair_poff[b->npairs] = (int)off;
-  b->nprimpairs = off;
+  b->h_pair_poff.assign(b->npairs + 1, 0);
+  b->h_pair_np.assign(std::max<int64_t>(b->npairs, 1), 0);
+  for (int64_t i = 0; i < b->npairs; ++i) b->h_pair_np[i] = b->h_nprim[b->h_pair_a[i]] * b->h_nprim[b->h_pair_b[i]];
+  int64_t slot = 0;  // in double2 units
+  auto layout = [&](int lo, int hi) {
+    for (int t0 = lo; t0 < hi; t0 += TILE_KET) {
+      int kmax = 0;
+      for (int i = t0; i < std::min(hi, t0 + TILE_KET); ++i) kmax = std::max(kmax, b->h_pair_np[i]);
+      for (int i = t0; i < std::min(hi, t0 + TILE_KET); ++i) b->h_pair_poff[i] = (int)(slot + (i - t0));
+      slot += (int64_t)3 * TILE_KET * kmax;
+    }
+  };
+  for (int c = 0; c < NCLASS; ++c) layout(b->class_off[c], b->class_off[c + 1]);
+  for (int c = 0; c < NCLASS; ++c) layout(b->ri_class_off[c], b->ri_class_off[c + 1]);
+  b->h_pair_poff[b->npairs] = (int)std::min<int64_t>(slot, 0x7fffffff);
+  b->nprimpairs = slot;  // double2 slots of the record buffer
 }
 
 }  // namespace qlb
@@ -277,7 +288,7 @@ extern "C" int qlb_basis_destroy(qlb_basis *b) {
   if (!b) return QLB_OK;
   if (g_engine.ready) cudaSetDevice(g_engine.device);
   void *ptrs[] = {b->d_xyz, b->d_exps, b->d_coefs, b->d_poff, b->d_boff, b->d_L, b->d_pair_a, b->d_pair_b,
-                  b->d_pair_poff, b->d_pair_ql, b->d_pair_Q, b->d_pp,
+                  b->d_pair_poff, b->d_pair_np, b->d_pair_ql, b->d_pair_Q, b->d_pp,
                   b->d_P, b->d_JK, b->d_H, b->d_dl, b->d_counters, b->d_gcounts};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -332,14 +343,15 @@ static int basis_build_pairs(qlb_basis *b) {
   if (int rc = upload(&b->d_pair_a, b->h_pair_a)) return rc;
   if (int rc = upload(&b->d_pair_b, b->h_pair_b)) return rc;
   if (int rc = upload(&b->d_pair_poff, b->h_pair_poff)) return rc;
-  QLB_CUDA(cudaMalloc((void **)&b->d_pp, std::max<int64_t>(b->nprimpairs, 1) * 3 * sizeof(double2)));
+  QLB_CUDA(cudaMalloc((void **)&b->d_pp, std::max<int64_t>(b->nprimpairs, 1) * sizeof(double2)));
+  if (int rc = upload(&b->d_pair_np, b->h_pair_np)) return rc;
   QLB_CUDA(cudaMalloc((void **)&b->d_pair_Q, std::max<int64_t>(b->npairs, 1) * sizeof(double)));
   QLB_CUDA(cudaMalloc((void **)&b->d_pair_ql, std::max<int64_t>(b->npairs, 1) * sizeof(int)));
   if (int rc = run_pair_prims(b)) return rc;
   // K2: Schwarz bounds per pair (the (aux, unit) pairs of an RI basis keep bound 0: they are never screened)
   QLB_CUDA(cudaMemsetAsync(b->d_pair_Q, 0, std::max<int64_t>(b->npairs, 1) * sizeof(double), e.stream));
   SchwarzParams sp;
-  sp.sh_xyz = b->d_xyz; sp.pair_a = b->d_pair_a; sp.pair_b = b->d_pair_b; sp.pair_poff = b->d_pair_poff;
+  sp.sh_xyz = b->d_xyz; sp.pair_a = b->d_pair_a; sp.pair_b = b->d_pair_b; sp.pair_poff = b->d_pair_poff; sp.pair_np = b->d_pair_np;
   fill_pp(b, sp.pp);
   sp.boys = e.d_boys; sp.Q = b->d_pair_Q;
   for (int c = 0; c < NCLASS; ++c) {
@@ -388,9 +400,17 @@ static int basis_build_pairs(qlb_basis *b) {
   b->h_pair_b.swap(nb);
   b->h_pair_Q.swap(nq);
   compute_pair_offsets(b);
+  if (b->nprimpairs > 0x7fffffff) {
+    set_error("too many primitive pairs for 32-bit offsets");
+    return QLB_ERR_ARG;
+  }
+  cudaFree(b->d_pp);  // the tile layout of the sorted order needs a different number of slots
+  b->d_pp = nullptr;
+  QLB_CUDA(cudaMalloc((void **)&b->d_pp, std::max<int64_t>(b->nprimpairs, 1) * sizeof(double2)));
   QLB_CUDA(cudaMemcpy(b->d_pair_a, b->h_pair_a.data(), b->npairs * sizeof(int), cudaMemcpyHostToDevice));
   QLB_CUDA(cudaMemcpy(b->d_pair_b, b->h_pair_b.data(), b->npairs * sizeof(int), cudaMemcpyHostToDevice));
   QLB_CUDA(cudaMemcpy(b->d_pair_poff, b->h_pair_poff.data(), (b->npairs + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  QLB_CUDA(cudaMemcpy(b->d_pair_np, b->h_pair_np.data(), b->npairs * sizeof(int), cudaMemcpyHostToDevice));
   QLB_CUDA(cudaMemcpy(b->d_pair_ql, b->h_pair_ql.data(), b->npairs * sizeof(int), cudaMemcpyHostToDevice));
   QLB_CUDA(cudaMemcpy(b->d_pair_Q, b->h_pair_Q.data(), b->npairs * sizeof(double), cudaMemcpyHostToDevice));
   if (int rc = run_pair_prims(b)) return rc;
@@ -499,7 +519,7 @@ void qlb::base_class_params(qlb_basis *b, ClassParams &prm) { base_params(b, prm
 static void base_params(qlb_basis *b, ClassParams &prm) {
   memset(&prm, 0, sizeof(prm));
   prm.sh_xyz = b->d_xyz; prm.sh_boff = b->d_boff; prm.nsh = b->nsh; prm.nbf = b->nbf;
-  prm.pair_a = b->d_pair_a; prm.pair_b = b->d_pair_b; prm.pair_poff = b->d_pair_poff; prm.pair_ql = b->d_pair_ql;
+  prm.pair_a = b->d_pair_a; prm.pair_b = b->d_pair_b; prm.pair_poff = b->d_pair_poff; prm.pair_np = b->d_pair_np; prm.pair_ql = b->d_pair_ql;
   fill_pp(b, prm.pp);
   prm.boys = g_engine.d_boys;
   prm.dl = b->d_dl;

@@ -56,7 +56,8 @@ struct ClassParams {
   // shell pairs (sorted by class, then Schwarz bound descending)
   const int *__restrict__ pair_a;
   const int *__restrict__ pair_b;
-  const int *__restrict__ pair_poff;   // npairs+1 primitive-pair offsets
+  const int *__restrict__ pair_poff;   // per pair: double2 index of field 0 of its first primitive record (tile layout)
+  const int *__restrict__ pair_np;     // per pair: number of primitive pairs
   const int *__restrict__ pair_ql;     // qlog(Q_ab)
   PrimPairs pp;
   const double *__restrict__ boys;
@@ -113,6 +114,7 @@ struct SchwarzParams {
   const int *__restrict__ pair_a;
   const int *__restrict__ pair_b;
   const int *__restrict__ pair_poff;
+  const int *__restrict__ pair_np;
   PrimPairs pp;
   const double *__restrict__ boys;
   int off, n;
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(64) schwarz_kernel(const __grid_constant__ Sch
   const int g = prm.off + i;
   const int sa = prm.pair_a[g], sb = prm.pair_b[g];
   PairRef pr;
-  pr.off = prm.pair_poff[g]; pr.n = prm.pair_poff[g + 1] - pr.off;
+  pr.off = prm.pair_poff[g]; pr.n = prm.pair_np[g];
   pr.Ax = prm.sh_xyz[3 * sa]; pr.Ay = prm.sh_xyz[3 * sa + 1]; pr.Az = prm.sh_xyz[3 * sa + 2];
   pr.Bx = prm.sh_xyz[3 * sb]; pr.By = prm.sh_xyz[3 * sb + 1]; pr.Bz = prm.sh_xyz[3 * sb + 2];
   double acc[NA * NB * NA * NB];

@@ -81,7 +81,7 @@ struct PrimPairs {
 
 struct PairRef {  // what one thread needs to know about one shell pair
   double Ax, Ay, Az, Bx, By, Bz;
-  int off, n;     // primitive-pair range
+  int off, n;     // double2 index of the first primitive record (tile layout, see eri_body.inc); primitive pairs
 };
 
 // non-axial normalisation factor of Cartesian component (x,y,z) of a shell with L = x+y+z

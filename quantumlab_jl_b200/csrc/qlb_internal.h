@@ -55,7 +55,7 @@ struct qlb_basis {
   std::vector<int> h_L, h_nprim, h_poff, h_boff;
   // pairs, sorted by class then Schwarz bound (descending)
   int64_t npairs = 0;
-  std::vector<int> h_pair_a, h_pair_b, h_pair_poff, h_pair_ql;
+  std::vector<int> h_pair_a, h_pair_b, h_pair_poff, h_pair_np, h_pair_ql;
   std::vector<double> h_pair_Q;
   int class_off[qlb::NCLASS + 1] = {0};
   // resolution of the identity: shells [0,n_orb) orbital, [n_orb, nsh-1) auxiliary, shell nsh-1 the unit s function;
@@ -69,7 +69,7 @@ struct qlb_basis {
   // device
   double *d_xyz = nullptr, *d_exps = nullptr, *d_coefs = nullptr;
   int *d_poff = nullptr, *d_boff = nullptr, *d_L = nullptr;
-  int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pair_poff = nullptr, *d_pair_ql = nullptr;
+  int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pair_poff = nullptr, *d_pair_np = nullptr, *d_pair_ql = nullptr;
   double *d_pair_Q = nullptr;
   double2 *d_pp = nullptr;  // 3 double2 per primitive pair: {p,Px} {Py,Pz} {k/p, 1/(2p)}
   int64_t nprimpairs = 0;
