@@ -121,6 +121,11 @@ int qlb_comm_unique_id(void *id128);
 int qlb_comm_init(const void *id128, int rank, int nranks);
 int qlb_comm_destroy(void);
 int qlb_allreduce_jk_device(qlb_basis *b, double *dJK /* 2*N*N contiguous */, void *stream);
+/* After the first build the work is dealt by a cost model fed with the all-rank per-class counters of the previous build
+ * (qlb_allreduce_jk_device sums them with a second, 84-double all-reduce).  qlb_schedule_pieces exposes that schedule:
+ * gcounts[2*qc] quartets, gcounts[2*qc+1] primitive quartets of class pair qc; npieces[qc] pieces (row subsets p, p+np, ..);
+ * owner[qc*nranks + p] = rank that evaluates piece p.  Pure host function (tests). */
+int qlb_schedule_pieces(const double *gcounts, int nranks, int32_t *npieces, int32_t *owner);
 
 /* ---- one-electron matrices (SpecialMatricesModule.jl:102-177) ---------------------------- */
 int qlb_overlap(qlb_basis *b, double *S);

@@ -563,6 +563,25 @@ static bool build_schedule(const double *gc, int rank, int nranks, std::vector<s
   return true;
 }
 
+// Exposes the schedule for inspection / tests: for each class pair the number of pieces and the owning rank of each
+// piece (owner[qc*nranks + p], -1 beyond npieces[qc]).  Pure host function: no device needed.
+extern "C" int qlb_schedule_pieces(const double *gcounts, int nranks, int32_t *npieces, int32_t *owner) {
+  if (!gcounts || !npieces || !owner || nranks < 1) return QLB_ERR_ARG;
+  for (int i = 0; i < NQCLASS; ++i) npieces[i] = 0;
+  for (int i = 0; i < NQCLASS * nranks; ++i) owner[i] = -1;
+  for (int r = 0; r < nranks; ++r) {
+    std::vector<std::pair<int, int>> mine[NQCLASS];
+    if (!build_schedule(gcounts, r, nranks, mine)) return QLB_ERR_ARG;
+    for (int qc = 0; qc < NQCLASS; ++qc)
+      for (const auto &pc : mine[qc]) {
+        if (pc.first < 0 || pc.first >= nranks || owner[qc * nranks + pc.first] != -1) return QLB_ERR_STATE;
+        owner[qc * nranks + pc.first] = r;
+        npieces[qc] = pc.second;
+      }
+  }
+  return QLB_OK;
+}
+
 // kernels launched per class-pair launch (split classes launch one kernel per ket-d component)
 static int launch_count_of(int X, int Y) {
   int la, lb, lc, ld;

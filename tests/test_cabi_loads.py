@@ -50,3 +50,33 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 for pat in ("import oracle", "from oracle", "liboracle", "ql_oracle", "orc_"):
                     assert pat not in src, (f, pat)
+
+
+def test_multirank_schedule_covers_every_piece_once():
+    """The feedback schedule is a pure host function: every piece of every class pair must have exactly
+    one owner, identically computed on every rank, and the modelled load must be balanced."""
+    import numpy as np
+
+    from quantumlab_jl_b200 import libqlb
+
+    lib = libqlb.load()
+    rng = np.random.default_rng(0)
+    # counters shaped like the (H2O)32 build: quartets and primitive quartets per class pair
+    for trial in range(5):
+        q = rng.integers(0, 4_000_000, 21).astype(np.float64)
+        q[rng.integers(0, 21, 3)] = 0  # some empty classes
+        gc = np.zeros(42)
+        gc[0::2] = q
+        gc[1::2] = q * rng.integers(1, 14, 21)
+        for nranks in (1, 2, 3, 4, 8):
+            npieces = np.zeros(21, dtype=np.int32)
+            owner = np.zeros(21 * nranks, dtype=np.int32)
+            rc = lib.qlb_schedule_pieces(libqlb.dptr(gc), nranks, libqlb.iptr(npieces), libqlb.iptr(owner))
+            assert rc == 0
+            owner = owner.reshape(21, nranks)
+            for qc in range(21):
+                assert 1 <= npieces[qc] <= nranks
+                assert (owner[qc, :npieces[qc]] >= 0).all() and (owner[qc, npieces[qc]:] == -1).all()
+                assert (owner[qc, :npieces[qc]] < nranks).all()
+            if nranks > 1:
+                assert len(set(owner[owner >= 0].tolist())) == nranks  # every rank got work
