@@ -531,7 +531,7 @@ static void base_params(qlb_basis *b, ClassParams &prm) {
 // ratios matter).  Every class pair is cut into 1..nranks pieces of about a third of a rank's share and the pieces
 // are assigned longest-first to the least loaded rank.  Pure function of (counts, nranks): identical on all ranks.
 static bool build_schedule(const double *gc, int rank, int nranks, std::vector<std::pair<int, int>> *mine) {
-  static const double eff[NQCLASS] = {3.28, 3.70, 6.38, 6.45, 12.19, 12.66, 5.07, 8.40, 14.16, 9.40, 10.34,
+  static const double eff[NQCLASS] = {3.63, 4.25, 7.10, 8.50, 12.19, 12.66, 5.95, 9.50, 14.16, 9.40, 11.30,
                                       11.57, 3.67, 9.26, 2.10, 11.90, 6.08, 3.18, 3.28, 2.58, 0.55};
   double cost[NQCLASS], total = 0.0;
   for (int X = 0; X < NCLASS; ++X)
