@@ -685,6 +685,10 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       const int nrows_local = vrank < nrows ? (nrows - vrank + vnranks - 1) / vnranks : 0;
       if (nrows_local == 0) continue;
       prm.nbx = (ket_eff + TILE_KET - 1) / TILE_KET;
+      // CTAs per bra tile row (ysplit): CTA y of a row walks ket tiles y, y+ysplit, ...  Enough CTAs for ~256 per SM
+      // (rows differ a lot in length), but >= 8 tiles per CTA when that still leaves >= 64 CTAs per SM, so the row's
+      // bra data are read once per many tiles.  (QLB_YS_TARGET / QLB_YS_TILES / QLB_YSPLIT_FULL: tuning knobs; the
+      // result was insensitive to them: 65.3-65.9 ms over a 16x range.)
       static const int ys_target = getenv("QLB_YS_TARGET") ? atoi(getenv("QLB_YS_TARGET")) : 256;
       static const int ys_tiles = getenv("QLB_YS_TILES") ? atoi(getenv("QLB_YS_TILES")) : 8;
       int ysplit = (int)std::min<int64_t>(prm.nbx, ((int64_t)e.sm_count * ys_target + nrows_local - 1) / nrows_local);
