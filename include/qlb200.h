@@ -150,6 +150,7 @@ int qlb_ri_eri_tensor(qlb_ri *r, double *out); /* B B^T as N^4 (computeTensorEle
 int qlb_ri_build_jk(qlb_ri *r, const double *P, double *J, double *K, double *ms);
 
 /* ---- knobs ---------------------------------------------------------------------------------------------- */
+int qlb_qlog(double x);        /* the integer screening rule's qlog(x) = ceil(8 log2 x), exact table form (tests) */
 int qlb_set_profiling(int on); /* time every class kernel with its own event pair (serialises the classes) */
 int qlb_fp64_peak_probe(double *tflops); /* DFMA microbenchmark: the measured FP64 roofline denominator */
 

@@ -249,6 +249,9 @@ extern "C" int qlb_device_info(char *name, int name_len, int *sm_count, int *cc_
   return QLB_OK;
 }
 
+// the quantised log used by the screening rule (host evaluation of the same inline function the kernels use)
+extern "C" int qlb_qlog(double x) { return qlog_exact(x); }
+
 extern "C" int qlb_set_profiling(int on) {
   g_engine.profiling = on != 0;
   return QLB_OK;

@@ -65,7 +65,7 @@ EXPORTS = (
     "qlb_build_jk_device", "qlb_symmetrize_device", "qlb_fock_device", "qlb_comm_unique_id", "qlb_comm_init",
     "qlb_comm_destroy", "qlb_allreduce_jk_device", "qlb_overlap", "qlb_kinetic", "qlb_nuclear_attraction",
     "qlb_set_profiling", "qlb_fp64_peak_probe", "qlb_ri_create", "qlb_ri_destroy", "qlb_ri_naux", "qlb_ri_b_tensor",
-    "qlb_ri_eri_tensor", "qlb_ri_build_jk", "qlb_schedule_pieces",
+    "qlb_ri_eri_tensor", "qlb_ri_build_jk", "qlb_schedule_pieces", "qlb_qlog",
 )
 
 
@@ -101,6 +101,8 @@ def load():
     lib.qlb_kinetic.argtypes = [C.c_void_p, _dp]
     lib.qlb_nuclear_attraction.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
     lib.qlb_set_profiling.argtypes = [C.c_int]
+    lib.qlb_qlog.argtypes = [C.c_double]
+    lib.qlb_qlog.restype = C.c_int
     lib.qlb_schedule_pieces.argtypes = [_dp, C.c_int, _ip, _ip]
     lib.qlb_ri_create.argtypes = [C.c_void_p, C.c_int, _dp, _ip, _ip, _dp, _dp, C.POINTER(C.c_void_p)]
     lib.qlb_ri_destroy.argtypes = [C.c_void_p]

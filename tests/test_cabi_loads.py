@@ -80,3 +80,26 @@ def test_multirank_schedule_covers_every_piece_once():
                 assert (owner[qc, :npieces[qc]] < nranks).all()
             if nranks > 1:
                 assert len(set(owner[owner >= 0].tolist())) == nranks  # every rank got work
+
+
+def test_qlog_bit_exact_between_library_and_oracle(orc):
+    """Screening counts can only be bit-exact if the library and the oracle quantise bounds identically: compare the
+    two independent implementations of qlog(x) = ceil(8 log2 x) on random values, bin edges and special values."""
+    import math
+
+    import numpy as np
+
+    from quantumlab_jl_b200 import libqlb
+
+    lib = libqlb.load()
+    rng = np.random.default_rng(1)
+    xs = list(10.0 ** rng.uniform(-290, 300, 20000)) + list(rng.uniform(0.5, 2.0, 20000))
+    for k in range(-64, 65):  # exact bin edges 2^(k/8) and their neighbours
+        e = 2.0 ** (k / 8.0)
+        xs += [e, math.nextafter(e, 0.0), math.nextafter(e, math.inf)]
+    xs += [0.0, -1.0, 1e-310, 1e-300, 1.0, 2.0, 0.5, float("inf"), 1.7976931348623157e308]
+    for x in xs:
+        assert lib.qlb_qlog(x) == orc.qlog(x), x
+    # and it is ceil(8 log2 x) away from the last-ulp neighbourhood of a bin edge
+    for x in (1e-12, 3.7, 123.456, 1e-5, 0.3, 7.0):
+        assert lib.qlb_qlog(x) == math.ceil(8 * math.log2(x))
