@@ -421,6 +421,8 @@ def run_ours(args):
         try:
             if args.cpu_seconds <= 0:
                 raise RuntimeError("skipped (--cpu-seconds 0)")
+            if world > 1:
+                raise RuntimeError("reported at N=1 only")
             v, desc, _ = cpu_reference_sample(shells, P, args.cpu_seconds, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
             vf, descf, thr = cpu_fair_sample(shells, P, args.tau, args.cpu_seconds)
