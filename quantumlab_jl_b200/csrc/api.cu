@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <numeric>
 
 #include "qlb_internal.h"
@@ -460,6 +461,13 @@ int qlb::basis_create_internal(int nsh, const double *centers, const int32_t *L,
   }
   b->nprim_total = b->h_poff[nsh];
   b->nbf = b->h_boff[nsh];
+  if (n_orb == 0)  // public entry: every primitive needs a positive, finite exponent (the RI unit function is internal)
+    for (int i = 0; i < b->nprim_total; ++i)
+      if (!(exps[i] > 0.0) || !std::isfinite(exps[i]) || !std::isfinite(coefs[i])) {
+        set_error("qlb_basis_create: exponents must be positive and finite, coefficients finite");
+        delete b;
+        return QLB_ERR_ARG;
+      }
   b->h_exps.assign(exps, exps + b->nprim_total);
   b->h_coefs.assign(coefs, coefs + b->nprim_total);
   int rc = QLB_OK;
