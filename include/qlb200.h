@@ -37,6 +37,7 @@ extern "C" {
 #define QLB_MAX_L 2         /* highest shell angular momentum with ERI class kernels (s,p,d) */
 #define QLB_NCLASS 6        /* shell-pair classes ss,ps,pp,ds,dp,dd                          */
 #define QLB_NQCLASS 21      /* canonical (bra class >= ket class) quartet classes            */
+#define QLB_JK_TAIL 64      /* doubles behind [J;K] that carry the schedule feedback through the one all-reduce */
 
 typedef struct qlb_basis qlb_basis; /* opaque: device-resident shells, shell pairs, Schwarz bounds */
 
@@ -101,6 +102,11 @@ int qlb_schwarz(qlb_basis *b, double *Q);
 int qlb_build_jk(qlb_basis *b, const double *P, double tau, double *J, double *K, qlb_stats *stats);
 int qlb_fock(qlb_basis *b, const double *H, const double *P, double tau, double *F, qlb_stats *stats);
 
+/* Tensor flavour of computeMatrixCoulomb / computeMatrixExchange (SpecialMatricesModule.jl:227-229, 264-266): contracts a
+ * STORED N^4 tensor T[mu,nu,la,si] (host, N <= 160) with P on the device.  exchange == 0: J[mu,nu] = sum T[mu,nu,la,si] P[la,si];
+ * exchange != 0: K[mu,nu] = sum T[mu,la,nu,si] P[la,si]. */
+int qlb_tensor_contract(int N, const double *T, const double *P, int exchange, double *out);
+
 /* Device-resident variant for callers that keep P/J/K in HBM (one process per GPU):
  * dP, dJ, dK are DEVICE pointers (N x N doubles).  Only the quartet tiles owned by `rank` of `nranks` are
  * evaluated, dJ/dK receive the rank's PARTIAL, un-symmetrised sums (J, K as defined above are obtained by
@@ -120,12 +126,13 @@ int qlb_fock_device(qlb_basis *b, const double *dH, const double *dJ, const doub
 int qlb_comm_unique_id(void *id128);
 int qlb_comm_init(const void *id128, int rank, int nranks);
 int qlb_comm_destroy(void);
-int qlb_allreduce_jk_device(qlb_basis *b, double *dJK /* 2*N*N contiguous */, void *stream);
-/* After the first build the work is dealt by a cost model fed with the all-rank per-class counters of the previous build
- * (qlb_allreduce_jk_device sums them with a second, 84-double all-reduce).  qlb_schedule_pieces exposes that schedule:
- * gcounts[2*qc] quartets, gcounts[2*qc+1] primitive quartets of class pair qc; npieces[qc] pieces (row subsets p, p+np, ..);
- * owner[qc*nranks + p] = rank that evaluates piece p.  Pure host function (tests). */
-int qlb_schedule_pieces(const double *gcounts, int nranks, int32_t *npieces, int32_t *owner);
+int qlb_allreduce_jk_device(qlb_basis *b, double *dJK /* 2*N*N + QLB_JK_TAIL doubles, contiguous */, void *stream);
+/* The first sharded build of a basis deals bra tile rows round-robin and times every class kernel (calibration); later
+ * builds deal whole pieces of classes by measured cost: class time of the calibration build, scaled by the class's
+ * current work, all-rank sums of which ride in the QLB_JK_TAIL doubles behind [J;K] through the SAME all-reduce.
+ * qlb_schedule_pieces exposes that schedule: cost[qc] (any unit) of class pair qc; npieces[qc] pieces (row subsets
+ * p, p+np, ..); owner[qc*nranks + p] = rank that evaluates piece p.  Pure host function (tests). */
+int qlb_schedule_pieces(const double *cost, int nranks, int32_t *npieces, int32_t *owner);
 
 /* ---- one-electron matrices (SpecialMatricesModule.jl:102-177) ---------------------------- */
 int qlb_overlap(qlb_basis *b, double *S);
@@ -149,10 +156,37 @@ int qlb_ri_b_tensor(qlb_ri *r, double *B);
 int qlb_ri_eri_tensor(qlb_ri *r, double *out); /* B B^T as N^4 (computeTensorElectronRepulsionIntegralsRICoulomb :54-58), N <= 64 */
 int qlb_ri_build_jk(qlb_ri *r, const double *P, double *J, double *K, double *ms);
 
+/* ---- SCF step on the device (HartreeFockModule.jl:73-84, :14-41; SpecialMatricesModule.jl:284-290) --------
+ * A qlb_scf keeps S, T, V, P, J, K, F and the eigenvectors in HBM, so one Roothaan iteration moves four doubles to the
+ * host instead of three N x N matrices.
+ * qlb_scf_create       uploads S, T, V (N x N, host) once.
+ * qlb_scf_set_density  uploads the initial guess (computeDensityMatrixGuess, InitialGuessModule.jl:11-16).
+ * qlb_scf_build        J, K <- P in one fused screened pass (sharded + all-reduced over the communicator's ranks), then
+ *                      energies4 = {2 tr(TP), 2 tr(VP), 2 tr(JP), -tr(KP)}: computeEnergyHartreeFock (:25-35), Vnn excluded.
+ *                      incremental != 0: J(P) = J(P_prev) + J(P - P_prev) with a full rebuild every 8th build (8f-3).
+ * qlb_scf_step         F = T + V + 2J - K; eigen(Symmetric(F), Symmetric(S)) (cuSOLVER Dsygvd); P = Cocc Cocc^T with the
+ *                      library's own DMMA GEMM: evaluateSCFStep (:73-84).
+ * qlb_scf_get          what = 0 P, 1 F, 2 J, 3 K (N x N), 4 orbital energies (N), 5 orbital coefficients (N x N). */
+typedef struct qlb_scf qlb_scf;
+int qlb_scf_create(qlb_basis *b, const double *S, const double *T, const double *V, int nocc, qlb_scf **out);
+int qlb_scf_destroy(qlb_scf *s);
+int qlb_scf_set_density(qlb_scf *s, const double *P);
+int qlb_scf_build(qlb_scf *s, double tau, int incremental, double *energies4, qlb_stats *stats);
+int qlb_scf_step(qlb_scf *s);
+int qlb_scf_get(qlb_scf *s, int what, double *out);
+/* C = alpha op(A) op(B) + beta C on DEVICE pointers (column-major) with the library's hand-written FP64 tensor-core
+ * kernel (mma.sync m8n8k4 f64 = DMMA): the contraction engine of qlb_scf_step and of the RI path; exported for tests. */
+int qlb_dgemm_device(int transA, int transB, int M, int N, int K, double alpha, const double *dA, int lda, const double *dB,
+                     int ldb, double beta, double *dC, int ldc, void *stream);
+
 /* ---- knobs ---------------------------------------------------------------------------------------------- */
 int qlb_qlog(double x);        /* the integer screening rule's qlog(x) = ceil(8 log2 x), exact table form (tests) */
 int qlb_set_profiling(int on); /* time every class kernel with its own event pair (serialises the classes) */
 int qlb_fp64_peak_probe(double *tflops); /* DFMA microbenchmark: the measured FP64 roofline denominator */
+/* Test hook: injects the schedule feedback a multi-rank run would have all-reduced (counts[2*qc] quartets,
+ * counts[2*qc+1] primitive quartets, class_ms[qc] calibration time of class pair qc), so that ONE device can evaluate
+ * every piece of the nranks-way deal with qlb_build_jk_device(rank = 0..nranks-1) and check that the pieces sum up. */
+int qlb_debug_set_schedule_feedback(qlb_basis *b, int nranks, const double *counts, const double *class_ms);
 
 #ifdef __cplusplus
 }

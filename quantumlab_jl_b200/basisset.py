@@ -34,6 +34,7 @@ class ContractedGaussianBasisFunctionDefinition:
 @dataclass
 class BasisSet:
     definitions: dict[Element, list[ContractedGaussianBasisFunctionDefinition]] = field(default_factory=dict)
+    name: str | None = None  # set by loadBasisSet: lets evaluateSCF find the SAD tables (InitialGuessModule.jl:95-105)
 
     def __class_getitem__(cls, name):  # BasisSet["sto-3g"]
         return loadBasisSet(name)
@@ -101,5 +102,7 @@ def loadBasisSet(name: str) -> BasisSet:
     key = _ALIASES.get(key, key)
     for cand in (name, os.path.join(_DATA, key + ".tx93")):
         if os.path.isfile(cand):
-            return readBasisSetTX93(cand)
+            bs = readBasisSetTX93(cand)
+            bs.name = {"6-31g_st": "6-31G*"}.get(key, key.upper())
+            return bs
     raise FileNotFoundError(f"basis set {name!r} is not vendored under {_DATA} (no network: see SURVEY.md 7.1)")

@@ -106,11 +106,6 @@ __global__ void fock_kernel(size_t n, const double *__restrict__ H, const double
   if (i < n) F[i] = H[i] + 2.0 * J[i] - K[i];
 }
 
-__global__ void counters_to_double_kernel(int n, const unsigned long long *__restrict__ c, double *out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (double)c[i];
-}
-
 __global__ void dfma_probe_kernel(double *out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
   const double m = 1.0000001, c = 1e-9;
@@ -212,8 +207,14 @@ extern "C" int qlb_init(int device) {
   make_boys_table(tab);
   QLB_CUDA(cudaMalloc((void **)&e.d_boys, tab.size() * sizeof(double)));
   QLB_CUDA(cudaMemcpy(e.d_boys, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
-  // the rolled high-L kernels keep their intermediates in local memory
-  cudaDeviceSetLimit(cudaLimitStackSize, 20 * 1024);
+  // the rolled kernels (tensor / RI / Schwarz use) keep their intermediates in local memory: the largest frame is the
+  // (dd|dd) Schwarz / rolled class kernel's (ptxas -v: 15.3 KB)
+  QLB_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024));
+  if (const char *v = getenv("QLB_YS_TARGET")) e.ys_target = std::max(1, atoi(v));
+  if (const char *v = getenv("QLB_YS_TILES")) e.ys_tiles = std::max(1, atoi(v));
+  e.ysplit_full = getenv("QLB_YSPLIT_FULL") != nullptr;
+  if (const char *v = getenv("QLB_BIN_W")) e.bin_width = std::max(1, atoi(v));
+  e.no_schedule = getenv("QLB_NO_SCHEDULE") != nullptr;
   e.ready = true;
   return QLB_OK;
 }
@@ -292,14 +293,16 @@ extern "C" int qlb_basis_destroy(qlb_basis *b) {
   if (!b) return QLB_OK;
   if (g_engine.ready) cudaSetDevice(g_engine.device);
   void *ptrs[] = {b->d_xyz, b->d_exps, b->d_coefs, b->d_poff, b->d_boff, b->d_L, b->d_pair_a, b->d_pair_b,
-                  b->d_pair_poff, b->d_pair_np, b->d_pair_ql, b->d_pair_Q, b->d_pp,
-                  b->d_P, b->d_JK, b->d_H, b->d_dl, b->d_counters, b->d_gcounts};
+                  b->d_pair_poff, b->d_pair_np, b->d_pair_ql, b->d_pair_qls, b->d_pair_Q, b->d_pp,
+                  b->d_P, b->d_JK, b->d_H, b->d_dl, b->d_counters, b->d_ms_local};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (auto &ev : b->ev)
     if (ev) cudaEventDestroy(ev);
   if (b->ev_gcounts) cudaEventDestroy(b->ev_gcounts);
+  if (b->ev_dlmax) cudaEventDestroy(b->ev_dlmax);
   if (b->h_gcounts) cudaFreeHost(b->h_gcounts);
+  if (b->h_dlmax) cudaFreeHost(b->h_dlmax);
   delete b;
   return QLB_OK;
 }
@@ -351,6 +354,7 @@ static int basis_build_pairs(qlb_basis *b) {
   if (int rc = upload(&b->d_pair_np, b->h_pair_np)) return rc;
   QLB_CUDA(cudaMalloc((void **)&b->d_pair_Q, std::max<int64_t>(b->npairs, 1) * sizeof(double)));
   QLB_CUDA(cudaMalloc((void **)&b->d_pair_ql, std::max<int64_t>(b->npairs, 1) * sizeof(int)));
+  QLB_CUDA(cudaMalloc((void **)&b->d_pair_qls, std::max<int64_t>(b->npairs, 1) * sizeof(int)));
   if (int rc = run_pair_prims(b)) return rc;
   // K2: Schwarz bounds per pair (the (aux, unit) pairs of an RI basis keep bound 0: they are never screened)
   QLB_CUDA(cudaMemsetAsync(b->d_pair_Q, 0, std::max<int64_t>(b->npairs, 1) * sizeof(double), e.stream));
@@ -367,31 +371,38 @@ static int basis_build_pairs(qlb_basis *b) {
   b->h_pair_Q.resize(b->npairs);
   QLB_CUDA(cudaMemcpyAsync(b->h_pair_Q.data(), b->d_pair_Q, b->npairs * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
   QLB_CUDA(cudaStreamSynchronize(e.stream));
-  // K3 (host part): sort each class by bound, descending; ties by original position (deterministic)
+  // K3 (host part): order the pairs of each class by COARSE Schwarz-bound bin (descending), then by shell indices.
+  // The bins keep the early exits of the kernels (walks end where the running maximum of the bounds, pair_qls, fails),
+  // the index order inside a bin makes the 32 consecutive ket pairs of a warp neighbours in the basis: their gathers of
+  // P / dl / shell data and their J/K reductions then fall into a few cache lines instead of 32 (ncu: the light classes
+  // were bound by exactly those L1 wavefronts).  The screening DECISION per quartet does not depend on the order.
   std::vector<int> perm(b->npairs);
   std::iota(perm.begin(), perm.end(), 0);
-  auto kbin = [&](int x) {
-    const int K = b->h_nprim[b->h_pair_a[x]] * b->h_nprim[b->h_pair_b[x]];
-    (void)K;
-    return 0;  // binning by contraction degree measured no gain (the Schwarz ordering already clusters similar K)
-  };
+  std::vector<int> ql0(b->npairs);
+  for (int64_t i = 0; i < b->npairs; ++i) ql0[i] = qlog_exact(b->h_pair_Q[i]);
+  const int binw = std::max(1, g_engine.bin_width);
   b->seg_off.clear();
   b->seg_cls.clear();
   for (int c = 0; c < NCLASS; ++c) {
+    int qmax = -32768;
+    for (int i = b->class_off[c]; i < b->class_off[c + 1]; ++i) qmax = std::max(qmax, ql0[i]);
+    auto bin = [&](int x) { return ql0[x] <= -32768 ? (1 << 28) : (qmax - ql0[x]) / binw; };
     std::stable_sort(perm.begin() + b->class_off[c], perm.begin() + b->class_off[c + 1], [&](int x, int y) {
-      const int kx = kbin(x), ky = kbin(y);
-      return kx != ky ? kx > ky : b->h_pair_Q[x] > b->h_pair_Q[y];
+      const int bx = bin(x), by = bin(y);
+      if (bx != by) return bx < by;
+      if (b->h_pair_a[x] != b->h_pair_a[y]) return b->h_pair_a[x] < b->h_pair_a[y];
+      return b->h_pair_b[x] < b->h_pair_b[y];
     });
-    for (int i = b->class_off[c]; i < b->class_off[c + 1]; ++i)
-      if (i == b->class_off[c] || kbin(perm[i]) != kbin(perm[i - 1])) {
-        b->seg_off.push_back(i);
-        b->seg_cls.push_back(c);
-      }
+    if (b->class_off[c + 1] > b->class_off[c]) {
+      b->seg_off.push_back(b->class_off[c]);
+      b->seg_cls.push_back(c);
+    }
   }
   b->seg_off.push_back(b->class_off[NCLASS]);
   std::vector<int> na(b->npairs), nb(b->npairs);
   std::vector<double> nq(b->npairs);
   b->h_pair_ql.resize(b->npairs);
+  b->h_pair_qls.resize(b->npairs);
   b->qlmax = -32768;
   for (int64_t i = 0; i < b->npairs; ++i) {
     na[i] = b->h_pair_a[perm[i]];
@@ -400,6 +411,16 @@ static int basis_build_pairs(qlb_basis *b) {
     b->h_pair_ql[i] = qlog_exact(nq[i]);
     b->qlmax = std::max(b->qlmax, b->h_pair_ql[i]);
   }
+  // pair_qls: running maximum from the END of each class (and RI group): bounds this pair and every later one
+  auto suffix_max = [&](int lo, int hi) {
+    int m = -32768;
+    for (int i = hi - 1; i >= lo; --i) {
+      m = std::max(m, b->h_pair_ql[i]);
+      b->h_pair_qls[i] = m;
+    }
+  };
+  for (int c = 0; c < NCLASS; ++c) suffix_max(b->class_off[c], b->class_off[c + 1]);
+  for (int c = 0; c < NCLASS; ++c) suffix_max(b->ri_class_off[c], b->ri_class_off[c + 1]);
   b->h_pair_a.swap(na);
   b->h_pair_b.swap(nb);
   b->h_pair_Q.swap(nq);
@@ -416,6 +437,7 @@ static int basis_build_pairs(qlb_basis *b) {
   QLB_CUDA(cudaMemcpy(b->d_pair_poff, b->h_pair_poff.data(), (b->npairs + 1) * sizeof(int), cudaMemcpyHostToDevice));
   QLB_CUDA(cudaMemcpy(b->d_pair_np, b->h_pair_np.data(), b->npairs * sizeof(int), cudaMemcpyHostToDevice));
   QLB_CUDA(cudaMemcpy(b->d_pair_ql, b->h_pair_ql.data(), b->npairs * sizeof(int), cudaMemcpyHostToDevice));
+  QLB_CUDA(cudaMemcpy(b->d_pair_qls, b->h_pair_qls.data(), b->npairs * sizeof(int), cudaMemcpyHostToDevice));
   QLB_CUDA(cudaMemcpy(b->d_pair_Q, b->h_pair_Q.data(), b->npairs * sizeof(double), cudaMemcpyHostToDevice));
   if (int rc = run_pair_prims(b)) return rc;
   QLB_CUDA(cudaStreamSynchronize(e.stream));
@@ -479,7 +501,7 @@ int qlb::basis_create_internal(int nsh, const double *centers, const int32_t *L,
   const size_t N2 = (size_t)b->nbf * b->nbf;
   cudaError_t ce;
   if ((ce = cudaMalloc((void **)&b->d_P, N2 * sizeof(double))) != cudaSuccess ||
-      (ce = cudaMalloc((void **)&b->d_JK, 2 * N2 * sizeof(double))) != cudaSuccess ||
+      (ce = cudaMalloc((void **)&b->d_JK, (2 * N2 + QLB_JK_TAIL) * sizeof(double))) != cudaSuccess ||
       (ce = cudaMalloc((void **)&b->d_H, N2 * sizeof(double))) != cudaSuccess ||
       (ce = cudaMalloc((void **)&b->d_dl, ((size_t)nsh * nsh + 1) * sizeof(int))) != cudaSuccess ||
       (ce = cudaMalloc((void **)&b->d_counters, 2 * NQCLASS * sizeof(unsigned long long))) != cudaSuccess) {
@@ -488,8 +510,10 @@ int qlb::basis_create_internal(int nsh, const double *centers, const int32_t *L,
   }
   for (auto &ev : b->ev) cudaEventCreate(&ev);
   cudaEventCreateWithFlags(&b->ev_gcounts, cudaEventDisableTiming);
-  if ((ce = cudaMalloc((void **)&b->d_gcounts, 2 * NQCLASS * sizeof(double))) != cudaSuccess ||
-      (ce = cudaMallocHost((void **)&b->h_gcounts, 2 * NQCLASS * sizeof(double))) != cudaSuccess) {
+  cudaEventCreateWithFlags(&b->ev_dlmax, cudaEventDisableTiming);
+  if ((ce = cudaMalloc((void **)&b->d_ms_local, NQCLASS * sizeof(double))) != cudaSuccess ||
+      (ce = cudaMallocHost((void **)&b->h_dlmax, sizeof(int))) != cudaSuccess ||
+      (ce = cudaMallocHost((void **)&b->h_gcounts, 3 * NQCLASS * sizeof(double))) != cudaSuccess) {
     qlb_basis_destroy(b);
     return cuda_fail(ce, "cudaMalloc(gcounts)");
   }
@@ -530,37 +554,29 @@ void qlb::base_class_params(qlb_basis *b, ClassParams &prm) { base_params(b, prm
 static void base_params(qlb_basis *b, ClassParams &prm) {
   memset(&prm, 0, sizeof(prm));
   prm.sh_xyz = b->d_xyz; prm.sh_boff = b->d_boff; prm.nsh = b->nsh; prm.nbf = b->nbf;
-  prm.pair_a = b->d_pair_a; prm.pair_b = b->d_pair_b; prm.pair_poff = b->d_pair_poff; prm.pair_np = b->d_pair_np; prm.pair_ql = b->d_pair_ql;
+  prm.pair_a = b->d_pair_a; prm.pair_b = b->d_pair_b; prm.pair_poff = b->d_pair_poff; prm.pair_np = b->d_pair_np; prm.pair_ql = b->d_pair_ql; prm.pair_qls = b->d_pair_qls;
   fill_pp(b, prm.pp);
   prm.boys = g_engine.d_boys;
   prm.dl = b->d_dl;
   prm.nranks = 1;
 }
 
-// Cost model for dealing class pieces to ranks: algorithmic flops of the class (from the all-rank counters of the
-// previous build) divided by the class kernel's measured efficiency (TFLOP/s, round-1 measurements on B200; only the
-// ratios matter).  Every class pair is cut into 1..nranks pieces of about a third of a rank's share and the pieces
-// are assigned longest-first to the least loaded rank.  Pure function of (counts, nranks): identical on all ranks.
-static bool build_schedule(const double *gc, int rank, int nranks, std::vector<std::pair<int, int>> *mine) {
-  static const double eff[NQCLASS] = {3.63, 4.25, 7.10, 8.50, 12.19, 12.66, 5.95, 9.50, 14.16, 9.40, 11.30,
-                                      11.57, 3.67, 9.26, 2.10, 11.90, 6.08, 3.18, 3.28, 2.58, 0.55};
-  double cost[NQCLASS], total = 0.0;
-  for (int X = 0; X < NCLASS; ++X)
-    for (int Y = 0; Y <= X; ++Y) {
-      const int qc = qclass_of(X, Y);
-      double fp, fd;
-      class_flops(X, Y, fp, fd);
-      cost[qc] = (fp * gc[2 * qc + 1] + fd * gc[2 * qc]) / eff[qc];
-      total += cost[qc];
-    }
+// Dealing class pieces to ranks.  cost[qc] is the MEASURED cost of class pair qc (class kernel time of the calibration
+// build summed over the ranks, scaled by the class's current work): no compiled-in efficiency table.  Every class pair
+// is cut into 1..nranks pieces of about a third of a rank's share and the pieces are assigned longest-first to the least
+// loaded rank.  Pure function of (cost, nranks): identical on all ranks.
+static bool build_schedule(const double *cost, int rank, int nranks, std::vector<std::pair<int, int>> *mine) {
+  double total = 0.0;
+  for (int qc = 0; qc < NQCLASS; ++qc) total += std::max(cost[qc], 0.0);
   if (!(total > 0.0)) return false;
   struct Piece { double c; int qc, p, np; };
   std::vector<Piece> pieces;
   const double target = total / (3.0 * nranks);
   for (int qc = 0; qc < NQCLASS; ++qc) {
-    int np = (int)ceil(cost[qc] / target);
+    const double c = std::max(cost[qc], 0.0);
+    int np = (int)ceil(c / target);
     np = std::max(1, std::min(np, nranks));
-    for (int p = 0; p < np; ++p) pieces.push_back({cost[qc] / np, qc, p, np});
+    for (int p = 0; p < np; ++p) pieces.push_back({c / np, qc, p, np});
   }
   std::stable_sort(pieces.begin(), pieces.end(), [](const Piece &a, const Piece &b) { return a.c > b.c; });
   std::vector<double> load(nranks, 0.0);
@@ -576,13 +592,13 @@ static bool build_schedule(const double *gc, int rank, int nranks, std::vector<s
 
 // Exposes the schedule for inspection / tests: for each class pair the number of pieces and the owning rank of each
 // piece (owner[qc*nranks + p], -1 beyond npieces[qc]).  Pure host function: no device needed.
-extern "C" int qlb_schedule_pieces(const double *gcounts, int nranks, int32_t *npieces, int32_t *owner) {
-  if (!gcounts || !npieces || !owner || nranks < 1) return QLB_ERR_ARG;
+extern "C" int qlb_schedule_pieces(const double *cost, int nranks, int32_t *npieces, int32_t *owner) {
+  if (!cost || !npieces || !owner || nranks < 1) return QLB_ERR_ARG;
   for (int i = 0; i < NQCLASS; ++i) npieces[i] = 0;
   for (int i = 0; i < NQCLASS * nranks; ++i) owner[i] = -1;
   for (int r = 0; r < nranks; ++r) {
     std::vector<std::pair<int, int>> mine[NQCLASS];
-    if (!build_schedule(gcounts, r, nranks, mine)) return QLB_ERR_ARG;
+    if (!build_schedule(cost, r, nranks, mine)) return QLB_ERR_ARG;
     for (int qc = 0; qc < NQCLASS; ++qc)
       for (const auto &pc : mine[qc]) {
         if (pc.first < 0 || pc.first >= nranks || owner[qc * nranks + pc.first] != -1) return QLB_ERR_STATE;
@@ -593,20 +609,42 @@ extern "C" int qlb_schedule_pieces(const double *gcounts, int nranks, int32_t *n
   return QLB_OK;
 }
 
-// kernels launched per class-pair launch (split classes launch one kernel per ket-d component)
-static int launch_count_of(int X, int Y) {
-  int la, lb, lc, ld;
-  class_L(X, la, lb);
-  class_L(Y, lc, ld);
-  const int L = la + lb + lc + ld;
-  const bool split = (L >= 5) && ld >= 1;  // (dp|pp) (dp|dp) (dd|pp) (dd|dp) (dd|dd): see the Makefile policy table
-  return split ? ncart(ld) : 1;
+// work of a class pair in model flops: only used as a RELATIVE scale between two builds of the same class
+static double class_work(int qc, double nquart, double nprim) {
+  for (int X = 0; X < NCLASS; ++X)
+    for (int Y = 0; Y <= X; ++Y)
+      if (qclass_of(X, Y) == qc) {
+        double fp, fd;
+        class_flops(X, Y, fp, fd);
+        return fp * nprim + fd * nquart;
+      }
+  return 0.0;
 }
+
+// Test hook: injects the schedule feedback a real multi-rank run would have produced (all-rank counters and class times
+// of a calibration build), so that one device can evaluate every piece of the scheduled deal (tests/test_gpu_parity.py).
+extern "C" int qlb_debug_set_schedule_feedback(qlb_basis *b, int nranks, const double *counts /*2*NQCLASS*/, const double *class_ms /*NQCLASS*/) {
+  if (!b || !counts || !class_ms || nranks < 1) return QLB_ERR_ARG;
+  for (int i = 0; i < 2 * NQCLASS; ++i) b->h_gcounts[i] = counts[i];
+  for (int qc = 0; qc < NQCLASS; ++qc) {
+    b->calib_ms[qc] = class_ms[qc];
+    b->calib_work[qc] = class_work(qc, counts[2 * qc], counts[2 * qc + 1]);
+  }
+  b->calib_nranks = nranks;
+  b->gcounts_pending = true;
+  b->gcounts_nranks = nranks;
+  cudaEventRecord(b->ev_gcounts, g_engine.stream);
+  return QLB_OK;
+}
+
+// policy of a class pair (class_tu.cu, mode -1): bra pairs per CTA and kernels launched per class-pair launch
+static int tile_bra_of(int X, int Y) { return launch_class_kernel(X, Y, -1, 0, nullptr, ClassParams()) & 0xff; }
+static int launch_count_of(int X, int Y) { return launch_class_kernel(X, Y, -1, 0, nullptr, ClassParams()) >> 8; }
 
 // number of leading pairs of segment sg (sorted by bound, descending) with ql >= need
 static int prefix_count(const qlb_basis *b, int sg, int need) {
-  const int *lo = b->h_pair_ql.data() + b->seg_off[sg], *hi = b->h_pair_ql.data() + b->seg_off[sg + 1];
-  // descending order: first position with ql < need
+  const int *lo = b->h_pair_qls.data() + b->seg_off[sg], *hi = b->h_pair_qls.data() + b->seg_off[sg + 1];
+  // pair_qls is non-increasing: first position from which no pair reaches `need`
   return (int)(std::partition_point(lo, hi, [need](int q) { return q >= need; }) - lo);
 }
 
@@ -623,44 +661,70 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
   const int nsh = b->nsh, N = b->nbf;
   const size_t N2 = (size_t)N * N;
   const bool screen = tau > 0.0;
-  const bool prof = e.profiling && stats;
+  // a sharded build of a basis that has no calibration yet times its class kernels one by one (and so does profiling)
+  const bool calibrate = nranks > 1 && b->calib_nranks != nranks && !e.no_schedule;
+  const bool prof = (e.profiling && stats) || calibrate;
   int launches = 0;
   if (stats) cudaEventRecord(b->ev[0], s);
-  int dlmax = 0, tlog = -32768;
+  // The density bound (max over shell blocks of qlog|P|) never leaves the device: the kernels read it from dl[nsh*nsh].
+  // The host only needs it to SIZE the grids, for which the previous build's value (+ one binary order of margin) does;
+  // the kernels walk rows with a grid stride and end on the sorted bounds, so a stale value cannot lose a quartet.
+  int dl_guess = 1 << 20, tlog = -32768;
   if (screen) {
+    if (b->dlmax_pending) {
+      QLB_CUDA(cudaEventSynchronize(b->ev_dlmax));  // recorded a whole build ago: already complete
+      dl_guess = *b->h_dlmax + 8;
+    }
     const int init = -32768;
     QLB_CUDA(cudaMemcpyAsync(b->d_dl + (size_t)nsh * nsh, &init, sizeof(int), cudaMemcpyHostToDevice, s));
     const int threads = 128, blocks = (nsh * nsh + threads - 1) / threads;
     density_block_max_kernel<<<blocks, threads, 0, s>>>(nsh, N, b->d_boff, dP, b->d_dl);
     QLB_CUDA(cudaGetLastError());
     ++launches;
-    QLB_CUDA(cudaMemcpyAsync(&dlmax, b->d_dl + (size_t)nsh * nsh, sizeof(int), cudaMemcpyDeviceToHost, s));
-    QLB_CUDA(cudaStreamSynchronize(s));
+    QLB_CUDA(cudaMemcpyAsync(b->h_dlmax, b->d_dl + (size_t)nsh * nsh, sizeof(int), cudaMemcpyDeviceToHost, s));
+    QLB_CUDA(cudaEventRecord(b->ev_dlmax, s));
+    b->dlmax_pending = true;
     tlog = qlog_exact(tau);
   }
   QLB_CUDA(cudaMemsetAsync(dJ, 0, N2 * sizeof(double), s));
   QLB_CUDA(cudaMemsetAsync(dK, 0, N2 * sizeof(double), s));
   QLB_CUDA(cudaMemsetAsync(b->d_counters, 0, 2 * NQCLASS * sizeof(unsigned long long), s));
   const int nseg = (int)b->seg_cls.size();
-  std::vector<int> nsig(nseg);
-  int64_t pairs_sig = 0;
-  for (int sg = 0; sg < nseg; ++sg) {
-    nsig[sg] = screen ? prefix_count(b, sg, tlog - b->qlmax - dlmax) : b->seg_off[sg + 1] - b->seg_off[sg];
-    pairs_sig += nsig[sg];
-  }
+  // pairs that can survive at all (grid sizing only)
+  auto sig_count = [&](int sg, int dlmax) {
+    const int n = b->seg_off[sg + 1] - b->seg_off[sg];
+    if (!screen) return n;
+    const int64_t need = (int64_t)tlog - b->qlmax - dlmax;
+    return need < -40000 ? n : prefix_count(b, sg, (int)need);
+  };
   ClassParams prm;
   base_params(b, prm);
-  prm.tlog = tlog; prm.dlmax = dlmax; prm.screen = screen ? 1 : 0;
+  prm.tlog = tlog; prm.screen = screen ? 1 : 0;
   prm.rank = rank; prm.nranks = nranks;
   prm.P = dP; prm.J = dJ; prm.K = dK;
   if (stats) cudaEventRecord(b->ev[1], s);
   bool qc_started[NQCLASS] = {false};
-  // ---- multi-rank schedule from the previous build's all-rank counters (identical on every rank)
+  // ---- multi-rank schedule from measured class costs (identical on every rank)
   std::vector<std::pair<int, int>> my_pieces[NQCLASS];  // per class pair: (piece index, number of pieces)
   bool scheduled = false;
-  if (nranks > 1 && b->gcounts_pending && b->gcounts_nranks == nranks && !getenv("QLB_NO_SCHEDULE")) {
-    QLB_CUDA(cudaEventSynchronize(b->ev_gcounts));
-    scheduled = build_schedule(b->h_gcounts, rank, nranks, my_pieces);
+  if (nranks > 1 && !calibrate && b->gcounts_pending && b->gcounts_nranks == nranks && !e.no_schedule) {
+    QLB_CUDA(cudaEventSynchronize(b->ev_gcounts));  // the previous build's all-reduce: long complete
+    if (b->calib_work[0] == 0.0 && b->calib_ms[0] == 0.0) {
+      // first build after the calibration build: adopt its all-rank class times and work
+      bool any = false;
+      for (int qc = 0; qc < NQCLASS; ++qc) {
+        b->calib_ms[qc] = b->h_gcounts[2 * NQCLASS + qc];
+        b->calib_work[qc] = class_work(qc, b->h_gcounts[2 * qc], b->h_gcounts[2 * qc + 1]);
+        any = any || b->calib_ms[qc] > 0.0;
+      }
+      if (!any) b->calib_nranks = 0;  // nothing was measured: calibrate again
+    }
+    double cost[NQCLASS];
+    for (int qc = 0; qc < NQCLASS; ++qc) {
+      const double w = class_work(qc, b->h_gcounts[2 * qc], b->h_gcounts[2 * qc + 1]);
+      cost[qc] = b->calib_work[qc] > 0.0 ? b->calib_ms[qc] * (w / b->calib_work[qc]) : (w > 0.0 ? 1e-3 : 0.0);
+    }
+    scheduled = b->calib_nranks == nranks && build_schedule(cost, rank, nranks, my_pieces);
   }
   bool forked = false;
   int nlaunch_classes = 0;
@@ -675,14 +739,18 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
     for (int sx = cls_seg[X + 1] - 1; sx >= cls_seg[X]; --sx)
      for (int sy = (X == Y ? sx : cls_seg[Y + 1] - 1); sy >= cls_seg[Y]; --sy) {
       const int qc = qclass_of(X, Y);
-      if (nsig[sx] == 0 || nsig[sy] == 0) continue;
-      prm.bra_off = b->seg_off[sx]; prm.bra_n = nsig[sx];
-      prm.ket_off = b->seg_off[sy]; prm.ket_n = nsig[sy];
+      // the kernels see the whole segments; the significant prefixes below only size the grid
+      prm.bra_off = b->seg_off[sx]; prm.bra_n = b->seg_off[sx + 1] - b->seg_off[sx];
+      prm.ket_off = b->seg_off[sy]; prm.ket_n = b->seg_off[sy + 1] - b->seg_off[sy];
+      if (prm.bra_n == 0 || prm.ket_n == 0) continue;
       prm.same = (sx == sy) ? 1 : 0;
-      int ket_eff = nsig[sy];
-      if (screen) ket_eff = std::min(ket_eff, prefix_count(b, sy, tlog - dlmax - b->h_pair_ql[b->seg_off[sx]]));
-      if (ket_eff == 0) continue;
-      if (prm.same) ket_eff = std::min(ket_eff, prm.bra_n);
+      prm.nbx = (prm.ket_n + TILE_KET - 1) / TILE_KET;
+      const int bra_sig = sig_count(sx, dl_guess);
+      int ket_eff = sig_count(sy, dl_guess);
+      if (screen && (int64_t)tlog - dl_guess > -40000)
+        ket_eff = std::min(ket_eff, prefix_count(b, sy, tlog - dl_guess - b->h_pair_qls[b->seg_off[sx]]));
+      if (bra_sig == 0 || ket_eff == 0) continue;  // (with the margin in dl_guess; the kernels would find nothing either)
+      if (prm.same) ket_eff = std::min(ket_eff, bra_sig);
       // unscheduled: tile rows are dealt round-robin over all ranks (the rank that receives row 0, the heaviest,
       // rotates with the class pair).  scheduled: this rank owns whole pieces (row subsets p, p+np, ...) of few classes
       std::vector<std::pair<int, int>> pieces;
@@ -692,21 +760,20 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       const int vrank = piece.first, vnranks = piece.second;
       prm.rank = vrank;
       prm.nranks = vnranks;
-      const int nrows = (prm.bra_n + TILE_BRA - 1) / TILE_BRA;
+      const int tile_bra = tile_bra_of(X, Y);
+      const int nrows = (bra_sig + tile_bra - 1) / tile_bra;
       const int nrows_local = vrank < nrows ? (nrows - vrank + vnranks - 1) / vnranks : 0;
       if (nrows_local == 0) continue;
-      prm.nbx = (ket_eff + TILE_KET - 1) / TILE_KET;
+      const int nbx_eff = (ket_eff + TILE_KET - 1) / TILE_KET;
       // CTAs per bra tile row (ysplit): CTA y of a row walks ket tiles y, y+ysplit, ...  Enough CTAs for ~256 per SM
       // (rows differ a lot in length), but >= 8 tiles per CTA when that still leaves >= 64 CTAs per SM, so the row's
-      // bra data are read once per many tiles.  (QLB_YS_TARGET / QLB_YS_TILES / QLB_YSPLIT_FULL: tuning knobs; the
-      // result was insensitive to them: 65.3-65.9 ms over a 16x range.)
-      static const int ys_target = getenv("QLB_YS_TARGET") ? atoi(getenv("QLB_YS_TARGET")) : 256;
-      static const int ys_tiles = getenv("QLB_YS_TILES") ? atoi(getenv("QLB_YS_TILES")) : 8;
-      int ysplit = (int)std::min<int64_t>(prm.nbx, ((int64_t)e.sm_count * ys_target + nrows_local - 1) / nrows_local);
-      const int ys_amort = std::max(1, prm.nbx / ys_tiles);
+      // bra data are read once per many tiles.  (QLB_YS_TARGET / QLB_YS_TILES / QLB_YSPLIT_FULL: tuning knobs read in
+      // qlb_init; the result was insensitive to them: 65.3-65.9 ms over a 16x range.)
+      int ysplit = (int)std::min<int64_t>(nbx_eff, ((int64_t)e.sm_count * e.ys_target + nrows_local - 1) / nrows_local);
+      const int ys_amort = std::max(1, nbx_eff / e.ys_tiles);
       if ((int64_t)nrows_local * ys_amort >= (int64_t)e.sm_count * 64) ysplit = std::min(ysplit, ys_amort);
       ysplit = std::max(1, ysplit);
-      if (getenv("QLB_YSPLIT_FULL")) ysplit = prm.nbx;
+      if (e.ysplit_full) ysplit = nbx_eff;
       prm.ysplit = ysplit;
       const int64_t grid = (int64_t)nrows_local * ysplit;
       prm.counters = b->d_counters + 2 * qc;
@@ -723,7 +790,15 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
         const int which = nlaunch_classes++ % (Engine::NSIDE + 1);
         if (which > 0) ls = e.side_stream[which - 1];
       }
-      if (int ce = launch_class_kernel(X, Y, 0, (unsigned)grid, ls, prm)) return cuda_fail((cudaError_t)ce, "eri_class_kernel");
+      const int ce = launch_class_kernel(X, Y, 0, (unsigned)grid, ls, prm);
+      if (ce) {
+        if (forked)  // join the side streams before reporting the failure
+          for (int i = 0; i < Engine::NSIDE; ++i) {
+            cudaEventRecord(e.ev_join[i], e.side_stream[i]);
+            cudaStreamWaitEvent(s, e.ev_join[i], 0);
+          }
+        return cuda_fail((cudaError_t)ce, "eri_class_kernel");
+      }
       if (prof) cudaEventRecord(b->ev[4 + 2 * qc + 1], s);
       launches += launch_count_of(X, Y);
      }  // pieces
@@ -733,35 +808,46 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       QLB_CUDA(cudaEventRecord(e.ev_join[i], e.side_stream[i]));
       QLB_CUDA(cudaStreamWaitEvent(s, e.ev_join[i], 0));
     }
-  if (stats) {
+  if (stats || calibrate) {
     cudaEventRecord(b->ev[2], s);
     unsigned long long h[2 * NQCLASS];
     QLB_CUDA(cudaMemcpyAsync(h, b->d_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
     QLB_CUDA(cudaStreamSynchronize(s));
-    memset(stats, 0, sizeof(*stats));
-    stats->quartets_unique = b->npairs * (b->npairs + 1) / 2;
-    stats->pairs_total = b->npairs;
-    stats->pairs_significant = pairs_sig;
-    stats->kernel_launches = launches;
-    for (int X = 0; X < NCLASS; ++X)
-      for (int Y = 0; Y <= X; ++Y) {
-        const int qc = qclass_of(X, Y);
-        stats->quartets_kept_class[qc] = (int64_t)h[2 * qc];
-        stats->prim_quartets_class[qc] = (int64_t)h[2 * qc + 1];
-        stats->quartets_kept += (int64_t)h[2 * qc];
-        double fp, fd;
-        class_flops(X, Y, fp, fd);
-        stats->flops_algorithmic += fp * (double)h[2 * qc + 1] + fd * (double)h[2 * qc];
-        if (prof && h[2 * qc]) {
-          float ms = 0;
-          if (cudaEventElapsedTime(&ms, b->ev[4 + 2 * qc], b->ev[4 + 2 * qc + 1]) == cudaSuccess) stats->ms_class[qc] = ms;
-        }
+    float msq[NQCLASS] = {0};
+    for (int qc = 0; qc < NQCLASS; ++qc)
+      if (prof && qc_started[qc]) cudaEventElapsedTime(&msq[qc], b->ev[4 + 2 * qc], b->ev[4 + 2 * qc + 1]);
+    if (calibrate) {  // this rank's class times ride to the other ranks in the tail of the [J;K] all-reduce
+      for (int qc = 0; qc < NQCLASS; ++qc) {
+        b->h_ms_local[qc] = msq[qc];
+        b->calib_ms[qc] = b->calib_work[qc] = 0.0;
       }
-    float ms = 0;
-    cudaEventElapsedTime(&ms, b->ev[0], b->ev[2]);
-    stats->ms_total = ms;
-    cudaEventElapsedTime(&ms, b->ev[1], b->ev[2]);
-    stats->ms_eri = ms;
+      b->ms_local_pending = true;
+      b->calib_nranks = nranks;
+    }
+    if (stats) {
+      memset(stats, 0, sizeof(*stats));
+      stats->quartets_unique = b->npairs * (b->npairs + 1) / 2;
+      stats->pairs_total = b->npairs;
+      const int dlmax_now = screen ? *b->h_dlmax : 0;  // this build's bound (the stream has been synchronised)
+      for (int sg = 0; sg < nseg; ++sg) stats->pairs_significant += sig_count(sg, dlmax_now);
+      stats->kernel_launches = launches;
+      for (int X = 0; X < NCLASS; ++X)
+        for (int Y = 0; Y <= X; ++Y) {
+          const int qc = qclass_of(X, Y);
+          stats->quartets_kept_class[qc] = (int64_t)h[2 * qc];
+          stats->prim_quartets_class[qc] = (int64_t)h[2 * qc + 1];
+          stats->quartets_kept += (int64_t)h[2 * qc];
+          double fp, fd;
+          class_flops(X, Y, fp, fd);
+          stats->flops_algorithmic += fp * (double)h[2 * qc + 1] + fd * (double)h[2 * qc];
+          if (prof && h[2 * qc]) stats->ms_class[qc] = msq[qc];
+        }
+      float ms = 0;
+      cudaEventElapsedTime(&ms, b->ev[0], b->ev[2]);
+      stats->ms_total = ms;
+      cudaEventElapsedTime(&ms, b->ev[1], b->ev[2]);
+      stats->ms_eri = ms;
+    }
   }
   return QLB_OK;
 }
@@ -852,7 +938,8 @@ static int tensor_device(qlb_basis *b, double *dT) {
       prm.same = (X == Y) ? 1 : 0;
       prm.nbx = (prm.ket_n + TILE_KET - 1) / TILE_KET;
       prm.ysplit = prm.nbx;
-      const int64_t grid = (int64_t)((prm.bra_n + TILE_BRA - 1) / TILE_BRA) * prm.nbx;
+      const int tile_bra = tile_bra_of(X, Y);
+      const int64_t grid = (int64_t)((prm.bra_n + tile_bra - 1) / tile_bra) * prm.nbx;
       if (int ce = launch_class_kernel(X, Y, 1, (unsigned)grid, e.stream, prm)) return cuda_fail((cudaError_t)ce, "eri_class_kernel(tensor)");
     }
   return QLB_OK;
@@ -997,6 +1084,15 @@ extern "C" int qlb_comm_destroy(void) {
   return QLB_OK;
 }
 
+// fills the QLB_JK_TAIL doubles behind [J;K]: per-class counters of this build and, after a calibration build, this
+// rank's class kernel times
+__global__ void jk_tail_kernel(const unsigned long long *__restrict__ c, const double *__restrict__ ms, double *tail) {
+  const int i = threadIdx.x;
+  if (i < 2 * NQCLASS) tail[i] = (double)c[i];
+  else if (i < 3 * NQCLASS) tail[i] = ms ? ms[i - 2 * NQCLASS] : 0.0;
+  else if (i < QLB_JK_TAIL) tail[i] = 0.0;
+}
+
 extern "C" int qlb_allreduce_jk_device(qlb_basis *b, double *dJK, void *stream_) {
   if (int rc = require_ready()) return rc;
   Engine &e = g_engine;
@@ -1005,15 +1101,20 @@ extern "C" int qlb_allreduce_jk_device(qlb_basis *b, double *dJK, void *stream_)
     set_error("qlb_allreduce_jk_device: no communicator (qlb_comm_init)");
     return QLB_ERR_STATE;
   }
+  static_assert(3 * NQCLASS <= QLB_JK_TAIL, "QLB_JK_TAIL too small");
   cudaStream_t s = stream_ ? (cudaStream_t)stream_ : e.stream;
   const size_t n = 2 * (size_t)b->nbf * b->nbf;
-  ncclResult_t r = p_AllReduce(dJK, dJK, n, ncclDouble, ncclSum, (ncclComm_t)e.nccl_comm, s);
+  // schedule feedback rides behind [J;K]: ONE collective per build
+  const double *dms = nullptr;
+  if (b->ms_local_pending) {
+    QLB_CUDA(cudaMemcpyAsync(b->d_ms_local, b->h_ms_local, NQCLASS * sizeof(double), cudaMemcpyHostToDevice, s));
+    dms = b->d_ms_local;
+    b->ms_local_pending = false;
+  }
+  jk_tail_kernel<<<1, QLB_JK_TAIL, 0, s>>>(b->d_counters, dms, dJK + n);
+  ncclResult_t r = p_AllReduce(dJK, dJK, n + QLB_JK_TAIL, ncclDouble, ncclSum, (ncclComm_t)e.nccl_comm, s);
   if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce");
-  // schedule feedback: the all-rank per-class quartet / primitive-quartet counts of this build (84 doubles)
-  counters_to_double_kernel<<<1, 64, 0, s>>>(2 * NQCLASS, b->d_counters, b->d_gcounts);
-  r = p_AllReduce(b->d_gcounts, b->d_gcounts, 2 * NQCLASS, ncclDouble, ncclSum, (ncclComm_t)e.nccl_comm, s);
-  if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce(counts)");
-  QLB_CUDA(cudaMemcpyAsync(b->h_gcounts, b->d_gcounts, 2 * NQCLASS * sizeof(double), cudaMemcpyDeviceToHost, s));
+  QLB_CUDA(cudaMemcpyAsync(b->h_gcounts, dJK + n, 3 * NQCLASS * sizeof(double), cudaMemcpyDeviceToHost, s));
   QLB_CUDA(cudaEventRecord(b->ev_gcounts, s));
   b->gcounts_pending = true;
   b->gcounts_nranks = e.nranks;

@@ -1,12 +1,20 @@
 // class_tu.cu -- one translation unit per canonical (ab|cd) class: compiled with
 //   -DQC_LA= -DQC_LB= -DQC_LC= -DQC_LD=   the four shell angular momenta
-//   -DQC_UNR=0|1                          rolled (local-memory) or fully unrolled (register) flavour of the J/K kernel
+//   -DQC_UNR=0|1|2                        flavour of the J/K (mode 0) and tensor (mode 1) kernel:
+//                                           0 rolled loops over local-memory arrays
+//                                           1 fully unrolled, register resident, one thread per quartet (x ket-d component)
+//                                           2 cooperative (eri_coop.cuh): ncart(LC) threads per quartet, R_tuv in shared memory
 //   -DQC_DSTEP=n                          ket-d components accumulated per pass (ncart(LD) = single pass)
-//   -DQC_MINB=n                           minimum resident CTAs per SM (register cap = 65536/(128 n))
-//   -DQC_SPLIT=0|1                        1: the J/K build of this class is ncart(LD) launches, one per ket-d component,
-//                                         each compiled in its own TU (this file again with -DQC_DSEL=k)
+//   -DQC_MINB=n                           minimum resident CTAs per SM (register cap)
+//   -DQC_SPLIT=0|1                        1: the class is ncart(LD) launches, one per ket-d component, each compiled in
+//                                         its own TU (this file again with -DQC_DSEL=k)
 // so that the classes build in parallel and each one's policy is a Makefile entry (see DESIGN.md "K4").
+// mode 2 (resolution-of-the-identity scatter) always runs the rolled flavour.
+// mode -1 is a query: returns (bra pairs per CTA) | (kernel launches per class launch) << 8 without launching.
 #include "qlb_internal.h"
+#if QC_UNR == 2
+#include "eri_coop.cuh"
+#endif
 
 #ifndef QC_MINB
 #define QC_MINB 1
@@ -19,51 +27,81 @@
 
 namespace qlb {
 
+#if QC_UNR == 2
+template <int MODE, int DSEL>
+static int launch_coop(unsigned grid, cudaStream_t s, const ClassParams &prm) {
+  using S = cop::CoopShape<QC_LA, QC_LB, QC_LC, QC_LD>;
+  auto kern = cop::eri_coop_kernel<QC_LA, QC_LB, QC_LC, QC_LD, MODE, DSEL, QC_MINB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  kern<<<grid, dim3(32, S::NW), S::SMEM_BYTES, s>>>(prm);
+  return (int)cudaGetLastError();
+}
+#endif
+
 #ifdef QC_DSEL
 // ---- one ket-d component of a split class
-int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, QC_DSEL)(unsigned grid, cudaStream_t s, const ClassParams &prm) {
+int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, QC_DSEL)(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm) {
+#if QC_UNR == 2
+  return mode == 0 ? launch_coop<0, QC_DSEL>(grid, s, prm) : launch_coop<1, QC_DSEL>(grid, s, prm);
+#else
   const dim3 block(TILE_KET, TILE_BRA);
 #if QC_UNR
-  unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, 1, QC_DSEL, QC_MINB><<<grid, block, 0, s>>>(prm);
+  if (mode == 0) unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, 1, QC_DSEL, QC_MINB><<<grid, block, 0, s>>>(prm);
+  else unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, 1, QC_DSEL, QC_MINB><<<grid, block, 0, s>>>(prm);
 #else
   // rolled split classes also split over the ket-c components (gridDim.y): 6x more, 6x shorter threads
-  rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, 1, QC_DSEL, QC_MINB, true><<<dim3(grid, ncart(QC_LC)), block, 0, s>>>(prm);
+  if (mode == 0) rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, 1, QC_DSEL, QC_MINB, true><<<dim3(grid, ncart(QC_LC)), block, 0, s>>>(prm);
+  else rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, 1, QC_DSEL, QC_MINB, false><<<grid, block, 0, s>>>(prm);
 #endif
   return (int)cudaGetLastError();
+#endif
 }
 #else
 #if QC_SPLIT
-int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 0)(unsigned grid, cudaStream_t s, const ClassParams &prm);
-int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 1)(unsigned grid, cudaStream_t s, const ClassParams &prm);
-int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 2)(unsigned grid, cudaStream_t s, const ClassParams &prm);
+int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 0)(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 1)(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 2)(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
 #if QC_LD >= 2
-int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 3)(unsigned grid, cudaStream_t s, const ClassParams &prm);
-int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 4)(unsigned grid, cudaStream_t s, const ClassParams &prm);
-int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 5)(unsigned grid, cudaStream_t s, const ClassParams &prm);
+int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 3)(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 4)(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 5)(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
 #endif
 #endif
 
 int QC_CAT(QC_LA, QC_LB, QC_LC, QC_LD)(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm) {
   const dim3 block(TILE_KET, TILE_BRA);
-  if (mode == 0) {
+  if (mode == -1) {
+    const int tile_bra = (QC_UNR == 2) ? 1 : TILE_BRA;
+    const int nlaunch = QC_SPLIT ? ncart(QC_LD) : 1;
+    return tile_bra | (nlaunch << 8);
+  }
+  if (mode == 0 || mode == 1) {
 #if QC_SPLIT
-    int rc = QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 0)(grid, s, prm);
-    if (!rc) rc = QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 1)(grid, s, prm);
-    if (!rc) rc = QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 2)(grid, s, prm);
+    int rc = QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 0)(mode, grid, s, prm);
+    if (!rc) rc = QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 1)(mode, grid, s, prm);
+    if (!rc) rc = QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 2)(mode, grid, s, prm);
 #if QC_LD >= 2
-    if (!rc) rc = QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 3)(grid, s, prm);
-    if (!rc) rc = QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 4)(grid, s, prm);
-    if (!rc) rc = QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 5)(grid, s, prm);
+    if (!rc) rc = QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 3)(mode, grid, s, prm);
+    if (!rc) rc = QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 4)(mode, grid, s, prm);
+    if (!rc) rc = QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 5)(mode, grid, s, prm);
 #endif
     return rc;
+#elif QC_UNR == 2
+    return mode == 0 ? launch_coop<0, 0>(grid, s, prm) : launch_coop<1, 0>(grid, s, prm);
 #elif QC_UNR
-    unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, QC_DSTEP, -1, QC_MINB><<<grid, block, 0, s>>>(prm);
+    if (mode == 0) unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, QC_DSTEP, -1, QC_MINB><<<grid, block, 0, s>>>(prm);
+    else unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, QC_DSTEP, -1, QC_MINB><<<grid, block, 0, s>>>(prm);
 #else
-    rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, QC_DSTEP, -1, QC_MINB><<<grid, block, 0, s>>>(prm);
+    if (mode == 0) rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, QC_DSTEP, -1, QC_MINB><<<grid, block, 0, s>>>(prm);
+    else rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, QC_DSTEP, -1, QC_MINB><<<grid, block, 0, s>>>(prm);
 #endif
-  } else if (mode == 1) {
-    rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, ncart(QC_LD)><<<grid, block, 0, s>>>(prm);
   } else {
+    // RI scatter (mode 2): rolled flavour, TILE_BRA bra pairs per CTA
     rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 2, ncart(QC_LD)><<<grid, block, 0, s>>>(prm);
   }
   return (int)cudaGetLastError();

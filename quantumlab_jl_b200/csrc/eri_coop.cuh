@@ -1,0 +1,563 @@
+// eri_coop.cuh -- the cooperative flavour of the ERI + J/K class kernels, for the high angular momentum classes
+// (total L >= 5) whose Hermite Coulomb integrals R_tuv (56..165 doubles per primitive quartet) do not fit the register
+// file next to the accumulators.
+//
+// Several threads per shell quartet: a CTA is ONE bra shell pair x 32 ket shell pairs (the lanes) x NW = ncart(LC)
+// warps; warp w owns ket-c Cartesian component w, the launch (template parameter DSEL) owns ket-d component DSEL, so a
+// thread accumulates the NA*NB integrals (a b | c_w d_DSEL) of its lane's quartet in registers.  Per primitive quartet
+//   1. every warp evaluates the Boys function and the one-index recursion R^n_{00v} for its lane (redundant, cheap),
+//      then builds the (u,v) columns of R_tuv dealt to it entirely in registers and parks them in SHARED memory
+//      (layout [t u v][lane]: conflict-free);
+//   2. after one barrier each thread contracts R with its own ket Hermite coefficients (static indices: one shared-
+//      memory load per R element, "scatter form") into G_tuv, then with the bra coefficients E^ab, which are CTA-uniform
+//      and sit in shared memory (broadcast loads), into the accumulators.
+// The bra-side Hermite coefficients are built once per CTA (one thread per bra primitive and axis).
+// Digestion: J_ab is reduced over the 32 lanes with a transposing shuffle tree (31 exchanges for 32 values), the
+// ket-indexed updates go out as FP64 reductions (RED) as in the register flavour.
+//
+// Replaces, like the other flavours, computeElectronRepulsionIntegral (IntegralsModule.jl:412-462) per quartet and
+// contractTensorBlocksWithMatrix_* (SpecialMatricesModule.jl:33-100).
+#pragma once
+#include <type_traits>
+#include <utility>
+
+#include "eri_kernels.cuh"
+
+namespace qlb {
+namespace cop {
+
+constexpr int COOP_MAXBP = 4;  // bra primitive pairs whose E^ab coefficients are resident in shared memory at a time
+
+__host__ __device__ constexpr int cart_x(int L, int idx) {
+  int i = 0;
+  for (int x = L; x >= 0; --x)
+    for (int y = L - x; y >= 0; --y, ++i)
+      if (i == idx) return x;
+  return 0;
+}
+__host__ __device__ constexpr int cart_y(int L, int idx) {
+  int i = 0;
+  for (int x = L; x >= 0; --x)
+    for (int y = L - x; y >= 0; --y, ++i)
+      if (i == idx) return y;
+  return 0;
+}
+
+// (t,u,v) of position idx in the tetrahedral layout hidx(L, ...)
+__host__ __device__ constexpr int herm_t(int L, int idx) {
+  for (int t = 0; t <= L; ++t)
+    for (int u = 0; u <= L - t; ++u)
+      for (int v = 0; v <= L - t - u; ++v)
+        if (hidx(L, t, u, v) == idx) return t;
+  return 0;
+}
+__host__ __device__ constexpr int herm_u(int L, int idx) {
+  for (int t = 0; t <= L; ++t)
+    for (int u = 0; u <= L - t; ++u)
+      for (int v = 0; v <= L - t - u; ++v)
+        if (hidx(L, t, u, v) == idx) return u;
+  return 0;
+}
+__host__ __device__ constexpr int herm_v(int L, int idx) {
+  for (int t = 0; t <= L; ++t)
+    for (int u = 0; u <= L - t; ++u)
+      for (int v = 0; v <= L - t - u; ++v)
+        if (hidx(L, t, u, v) == idx) return v;
+  return 0;
+}
+
+// compile-time loop: f(std::integral_constant<int, 0>) ... f(std::integral_constant<int, N-1>)
+template <class F, int... Is>
+__device__ __forceinline__ void static_for_impl(F &&f, std::integer_sequence<int, Is...>) {
+  (f(std::integral_constant<int, Is>()), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+  static_for_impl(f, std::make_integer_sequence<int, N>());
+}
+
+template <int LA, int LB, int LC, int LD>
+struct CoopShape {
+  static constexpr int NW = ncart(LC);
+  static constexpr int L = LA + LB + LC + LD, LAB = LA + LB, LCD = LC + LD;
+  static constexpr int NA = ncart(LA), NB = ncart(LB);
+  static constexpr int NE1 = (LA + 1) * (LB + 1) * (LAB + 1);  // E^ab entries per axis
+  static constexpr int R_DOUBLES = nherm(L) * 32;
+  static constexpr int E_DOUBLES = COOP_MAXBP * 3 * NE1;
+  static constexpr int B_DOUBLES = COOP_MAXBP * 8;
+  static constexpr int P_DOUBLES = NA * NB;
+  static constexpr size_t SMEM_BYTES = sizeof(double) * (R_DOUBLES + E_DOUBLES + B_DOUBLES + P_DOUBLES);
+};
+
+// ---- R_tuv columns.  S1[n][v] = R^n_{0,0,v}; column (u,v): R^0_{t,u,v}, t = 0..L-u-v, built from the v-th
+// two-index triangle A[n][u] = R^n_{0,u,v}.  Template recursion (not "#pragma unroll" on five nested triangular loops,
+// which nvcc gives up on and demotes the arrays to local memory) keeps every index a compile-time constant; a warp only
+// executes the columns it owns (warp-uniform branches on w).
+template <int L, int U, int V>
+__device__ __forceinline__ void r_column(const double (&S1)[L + 1][L + 1], double X, double Y, double *__restrict__ Rl) {
+  constexpr int M = L - U - V;
+  // two-index triangle of this v up to column U: A[n][uu], n + uu <= L - V
+  double A[L + 1][U + 1];
+#pragma unroll
+  for (int n = 0; n <= L - V; ++n) A[n][0] = S1[n][V];
+#pragma unroll
+  for (int uu = 1; uu <= U; ++uu) {
+#pragma unroll
+    for (int n = 0; n <= L - V - uu; ++n) {
+      double val = Y * A[n + 1][uu - 1];
+      if (uu > 1) val = fma((double)(uu - 1), A[n + 1][uu > 1 ? uu - 2 : 0], val);
+      A[n][uu] = val;
+    }
+  }
+  // t recursion on the column: B[n][t], n + t <= M
+  double B[M + 1][M + 1];
+#pragma unroll
+  for (int n = 0; n <= M; ++n) B[n][0] = A[n][U];
+#pragma unroll
+  for (int t = 1; t <= M; ++t) {
+#pragma unroll
+    for (int n = 0; n <= M - t; ++n) {
+      double val = X * B[n + 1][t - 1];
+      if (t > 1) val = fma((double)(t - 1), B[n + 1][t > 1 ? t - 2 : 0], val);
+      B[n][t] = val;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t <= M; ++t) Rl[hidx(L, t, U, V) * 32] = B[0][t];
+}
+
+// columns in order of decreasing length m = L-u-v (so that dealing them round-robin balances the warps):
+// column K -> (m, v): the m-th group has L-m+1 columns
+__host__ __device__ constexpr int col_m(int L, int K) {
+  int m = L, k = K;
+  while (k >= L - m + 1) { k -= L - m + 1; --m; }
+  return m;
+}
+__host__ __device__ constexpr int col_v(int L, int K) {
+  int m = L, k = K;
+  while (k >= L - m + 1) { k -= L - m + 1; --m; }
+  return k;
+}
+
+template <int L, int NW, int K>
+struct ColumnDeal {
+  static __device__ __forceinline__ void run(const double (&S1)[L + 1][L + 1], double X, double Y, int w, double *__restrict__ Rl) {
+    constexpr int M = col_m(L, K), V = col_v(L, K), U = L - M - V;
+    if ((K % NW) == w) r_column<L, U, V>(S1, X, Y, Rl);
+    if constexpr (K + 1 < (L + 1) * (L + 2) / 2) ColumnDeal<L, NW, K + 1>::run(S1, X, Y, w, Rl);
+  }
+};
+
+template <int L, int NW>
+__device__ __forceinline__ void build_R_columns(const double *Fs, double X, double Y, double Z, int w, double *__restrict__ Rl) {
+  double S1[L + 1][L + 1];
+#pragma unroll
+  for (int n = 0; n <= L; ++n) S1[n][0] = Fs[n];
+#pragma unroll
+  for (int v = 1; v <= L; ++v) {
+#pragma unroll
+    for (int n = 0; n <= L - v; ++n) {
+      double val = Z * S1[n + 1][v - 1];
+      if (v > 1) val = fma((double)(v - 1), S1[n + 1][v > 1 ? v - 2 : 0], val);
+      S1[n][v] = val;
+    }
+  }
+  ColumnDeal<L, NW, 0>::run(S1, X, Y, w, Rl);
+}
+
+__host__ __device__ constexpr bool r_has_target(int r, int s, int w, int bx, int by, int bz, int LAB) {
+  for (int tt = 0; tt <= bx; ++tt)
+    for (int uu = 0; uu <= by; ++uu)
+      for (int vv = 0; vv <= bz; ++vv) {
+        const int t = r - tt, u = s - uu, v = w - vv;
+        if (t >= 0 && u >= 0 && v >= 0 && t + u + v <= LAB) return true;
+      }
+  return false;
+}
+
+// ---- one thread's share of a primitive quartet: acc[a + NA*b] += (a b | c_IC d_ID)
+template <int LA, int LB, int LC, int LD, int IC, int ID>
+__device__ __forceinline__ void contract_cd(const double *__restrict__ Rl, const double *__restrict__ Es, double QCx,
+                                            double QDx, double QCy, double QDy, double QCz, double QDz, double oo2q,
+                                            double *acc) {
+  using S = CoopShape<LA, LB, LC, LD>;
+  constexpr int L = S::L, LAB = S::LAB, NA = S::NA, NE1 = S::NE1;
+  // ket Hermite coefficients (sign folded): only the rows of this thread's component pair survive dead-code elimination
+  double Ecd[3][LC + 1][LD + 1][LC + LD + 1];
+  unr::hermite_E<LC, LD, true>(Ecd[0], QCx, QDx, oo2q);
+  unr::hermite_E<LC, LD, true>(Ecd[1], QCy, QDy, oo2q);
+  unr::hermite_E<LC, LD, true>(Ecd[2], QCz, QDz, oo2q);
+  constexpr int cx = cart_x(LC, IC), cy = cart_y(LC, IC), cz = LC - cx - cy;
+  constexpr int dx = cart_x(LD, ID), dy = cart_y(LD, ID), dz = LD - dx - dy;
+  constexpr int bx = cx + dx, by = cy + dy, bz = cz + dz;
+  double ek[bx + 1][by + 1][bz + 1];
+#pragma unroll
+  for (int tt = 0; tt <= bx; ++tt)
+#pragma unroll
+    for (int uu = 0; uu <= by; ++uu) {
+      const double exy = Ecd[0][cx][dx][tt] * Ecd[1][cy][dy][uu];
+#pragma unroll
+      for (int vv = 0; vv <= bz; ++vv) ek[tt][uu][vv] = exy * Ecd[2][cz][dz][vv];
+    }
+  // ket contraction, scatter form: every needed R element is read from shared memory once
+  double G[nherm(LAB)];
+#pragma unroll
+  for (int i = 0; i < nherm(LAB); ++i) G[i] = 0.0;
+  static_for<nherm(L)>([&](auto ric) {
+    constexpr int ridx = decltype(ric)::value;
+    constexpr int r = herm_t(L, ridx), s = herm_u(L, ridx), w = herm_v(L, ridx);
+    if constexpr (r_has_target(r, s, w, bx, by, bz, LAB)) {
+      const double rv = Rl[ridx * 32];
+#pragma unroll
+      for (int tt = 0; tt <= bx; ++tt)
+#pragma unroll
+        for (int uu = 0; uu <= by; ++uu)
+#pragma unroll
+          for (int vv = 0; vv <= bz; ++vv) {
+            const int t = r - tt, u = s - uu, v = w - vv;
+            if (t >= 0 && u >= 0 && v >= 0 && t + u + v <= LAB)
+              G[hidx(LAB, t, u, v)] = fma(ek[tt][uu][vv], rv, G[hidx(LAB, t, u, v)]);
+          }
+    }
+  });
+  // bra contraction: E^ab is CTA-uniform (shared memory, broadcast loads)
+  const double *__restrict__ Ex = Es, *__restrict__ Ey = Es + NE1, *__restrict__ Ez = Es + 2 * NE1;
+  static_for<NA * S::NB>([&](auto abc) {
+    constexpr int iab = decltype(abc)::value, ia = iab % NA, ib = iab / NA;
+    constexpr int ax = cart_x(LA, ia), ay = cart_y(LA, ia), az = LA - ax - ay;
+    constexpr int bbx = cart_x(LB, ib), bby = cart_y(LB, ib), bbz = LB - bbx - bby;
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t <= ax + bbx; ++t)
+#pragma unroll
+      for (int u = 0; u <= ay + bby; ++u) {
+        const double exy = Ex[(ax * (LB + 1) + bbx) * (LAB + 1) + t] * Ey[(ay * (LB + 1) + bby) * (LAB + 1) + u];
+        double sv = 0.0;
+#pragma unroll
+        for (int v = 0; v <= az + bbz; ++v) sv = fma(Ez[(az * (LB + 1) + bbz) * (LAB + 1) + v], G[hidx(LAB, t, u, v)], sv);
+        s = fma(exy, sv, s);
+      }
+    acc[iab] += s;
+  });
+}
+
+// sum v[i] over the 32 lanes for i = 0..31 with a transposing tree: afterwards lane l holds the total of v[l].
+// 16+8+4+2+1 = 31 exchanges instead of 32*5.
+__device__ __forceinline__ double transpose_reduce32(double (&v)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      // lanes with bit h keep the upper half v[i+h], the others the lower half v[i]; the partner's copy is added
+      const double send = up ? v[i] : v[i + h];
+      const double keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return v[0];
+}
+// index of the value lane l ends up with after transpose_reduce32: bit h of the lane selected the upper half at step h
+__device__ __forceinline__ int transpose_reduce32_index(int lane) { return lane; }
+
+// ---- J/K digestion of one thread's (c_IC, d_ID) slice
+template <int LA, int LB, int LC, int LD, int IC, int ID>
+__device__ __forceinline__ void digest_cd(const double *acc, bool active, double deg, int fa, int fb, int fc, int fd,
+                                          const double *__restrict__ Pab, const ClassParams &prm) {
+  using S = CoopShape<LA, LB, LC, LD>;
+  constexpr int NA = S::NA, NB = S::NB;
+  constexpr int cx = cart_x(LC, IC), cy = cart_y(LC, IC), dx = cart_x(LD, ID), dy = cart_y(LD, ID);
+  const int N = prm.nbf;
+  const int lane = threadIdx.x;
+  const double *__restrict__ P = prm.P;
+  const int gc = fc + IC, gd = fd + ID;
+  // scaled integrals (non-axial factors, degeneracy); inactive lanes carry zeros
+  const double ncd = active ? nonaxial(LC, cx, cy, LC - cx - cy) * nonaxial(LD, dx, dy, LD - dx - dy) * deg : 0.0;
+  double I[NA * NB];
+  {
+    int ib = 0;
+#pragma unroll
+    for (int bx = LB; bx >= 0; --bx)
+#pragma unroll
+      for (int by = LB - bx; by >= 0; --by, ++ib) {
+        const double nb = nonaxial(LB, bx, by, LB - bx - by) * ncd;
+        int ia = 0;
+#pragma unroll
+        for (int ax = LA; ax >= 0; --ax)
+#pragma unroll
+          for (int ay = LA - ax; ay >= 0; --ay, ++ia) I[ia + NA * ib] = acc[ia + NA * ib] * (nonaxial(LA, ax, ay, LA - ax - ay) * nb);
+      }
+  }
+  if (active) {
+    const double pcd = __ldg(P + gc + (size_t)N * gd);
+    double jcd = 0.0;
+    double Kac[NA], Kad[NA], Kbc[NB], Kbd[NB];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) Kac[i] = Kad[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) Kbc[i] = Kbd[i] = 0.0;
+    double pad[NA], pac[NA];
+#pragma unroll
+    for (int ia = 0; ia < NA; ++ia) {
+      pad[ia] = __ldg(P + gd + (size_t)N * (fa + ia));
+      pac[ia] = __ldg(P + gc + (size_t)N * (fa + ia));
+    }
+#pragma unroll
+    for (int ib = 0; ib < NB; ++ib) {
+      const double pbd = __ldg(P + gd + (size_t)N * (fb + ib));
+      const double pbc = __ldg(P + gc + (size_t)N * (fb + ib));
+#pragma unroll
+      for (int ia = 0; ia < NA; ++ia) {
+        const double v = I[ia + NA * ib];
+        jcd = fma(v, Pab[ia + NA * ib], jcd);
+        Kac[ia] = fma(v, pbd, Kac[ia]);
+        Kad[ia] = fma(v, pbc, Kad[ia]);
+        Kbc[ib] = fma(v, pad[ia], Kbc[ib]);
+        Kbd[ib] = fma(v, pac[ia], Kbd[ib]);
+      }
+    }
+    atomicAdd(prm.J + gc + (size_t)N * gd, 0.5 * jcd);
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      atomicAdd(prm.K + gc + (size_t)N * (fa + i), 0.25 * Kac[i]);
+      atomicAdd(prm.K + gd + (size_t)N * (fa + i), 0.25 * Kad[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      atomicAdd(prm.K + gc + (size_t)N * (fb + i), 0.25 * Kbc[i]);
+      atomicAdd(prm.K + gd + (size_t)N * (fb + i), 0.25 * Kbd[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NA * NB; ++i) I[i] *= pcd;  // J_ab contribution of this (c,d)
+  }
+  // J_ab += sum over the 32 kets: transposing reduction in chunks of 32 values, then one RED per value
+#pragma unroll
+  for (int c0 = 0; c0 < NA * NB; c0 += 32) {
+    double v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (c0 + i < NA * NB) ? I[(c0 + i < NA * NB) ? c0 + i : 0] : 0.0;
+    if (NA * NB - c0 >= 8) {
+      const double tot = transpose_reduce32(v, lane);
+      const int i = c0 + lane;
+      if (i < NA * NB && tot != 0.0) atomicAdd(prm.J + (fa + i % NA) + (size_t)N * (fb + i / NA), 0.5 * tot);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (c0 + i >= NA * NB) break;
+        const double tot = warp_sum(v[i]);
+        if (lane == 0 && tot != 0.0) atomicAdd(prm.J + (fa + (c0 + i) % NA) + (size_t)N * (fb + (c0 + i) / NA), 0.5 * tot);
+      }
+    }
+  }
+}
+
+// ---- MODE 1: one thread's (c,d) slice into the N^4 tensor at its 8 symmetric positions
+template <int LA, int LB, int LC, int LD, int IC, int ID>
+__device__ __forceinline__ void scatter_cd(const double *acc, int fa, int fb, int fc, int fd, const ClassParams &prm) {
+  using S = CoopShape<LA, LB, LC, LD>;
+  constexpr int NA = S::NA;
+  constexpr int cx = cart_x(LC, IC), cy = cart_y(LC, IC), dx = cart_x(LD, ID), dy = cart_y(LD, ID);
+  const size_t N = prm.nbf;
+  double *T = prm.tensor;
+  const double ncd = nonaxial(LC, cx, cy, LC - cx - cy) * nonaxial(LD, dx, dy, LD - dx - dy);
+  const size_t c = fc + IC, d = fd + ID;
+  int ib = 0;
+#pragma unroll
+  for (int bx = LB; bx >= 0; --bx)
+#pragma unroll
+    for (int by = LB - bx; by >= 0; --by, ++ib) {
+      const double nb = nonaxial(LB, bx, by, LB - bx - by) * ncd;
+      int ia = 0;
+#pragma unroll
+      for (int ax = LA; ax >= 0; --ax)
+#pragma unroll
+        for (int ay = LA - ax; ay >= 0; --ay, ++ia) {
+          const double I = acc[ia + NA * ib] * (nonaxial(LA, ax, ay, LA - ax - ay) * nb);
+          const size_t a = fa + ia, b = fb + ib;
+          T[a + N * (b + N * (c + N * d))] = I;
+          T[b + N * (a + N * (c + N * d))] = I;
+          T[a + N * (b + N * (d + N * c))] = I;
+          T[b + N * (a + N * (d + N * c))] = I;
+          T[c + N * (d + N * (a + N * b))] = I;
+          T[d + N * (c + N * (a + N * b))] = I;
+          T[c + N * (d + N * (b + N * a))] = I;
+          T[d + N * (c + N * (b + N * a))] = I;
+        }
+    }
+}
+
+template <int LA, int LB, int LC, int LD, int MODE, int ID, int IC>
+struct CoopDispatch {  // warp w runs the code of ket-c component w
+  template <class F>
+  static __device__ __forceinline__ void run(int w, F &&f) {
+    if (w == IC) f(std::integral_constant<int, IC>());
+    else if constexpr (IC + 1 < ncart(LC)) CoopDispatch<LA, LB, LC, LD, MODE, ID, IC + 1>::run(w, f);
+  }
+};
+
+// MODE 0: J/K digestion with screening; MODE 1: tensor scatter (no screening).  DSEL: the ket-d component of this launch.
+template <int LA, int LB, int LC, int LD, int MODE, int DSEL, int MINB>
+__global__ void __launch_bounds__(32 * ncart(LC), MINB) eri_coop_kernel(const __grid_constant__ ClassParams prm) {
+  using S = CoopShape<LA, LB, LC, LD>;
+  constexpr int NW = S::NW, L = S::L, NA = S::NA, NB = S::NB, NE1 = S::NE1;
+  extern __shared__ double coop_smem[];
+  double *Rs = coop_smem;
+  double *Es = Rs + S::R_DOUBLES;
+  double *Bs = Es + S::E_DOUBLES;
+  double *Pab = Bs + S::B_DOUBLES;
+  const int lane = threadIdx.x, w = threadIdx.y, tid = w * 32 + lane;
+  const double *s_boys = prm.boys + (size_t)L * BOYS_TABLE_DOUBLES;
+  const int *__restrict__ dl = prm.dl;
+  const int nsh = prm.nsh;
+  const int dlmax = prm.screen ? dl[nsh * nsh] : 0;  // device-resident density bound (see eri_body.inc)
+  unsigned n_q = 0, n_pq = 0;
+  double *Rl = Rs + lane;
+  // CTA = one bra pair x every ysplit-th ket tile (32 ket pairs each); bra pairs are walked with a grid stride
+  const int y = blockIdx.x % prm.ysplit;
+  const int row_step = max(1, (int)gridDim.x / prm.ysplit);
+#pragma unroll 1
+  for (int rowl = blockIdx.x / prm.ysplit;; rowl += row_step) {
+  const int ib = rowl * prm.nranks + prm.rank;
+  if (ib >= prm.bra_n) break;
+  {
+    const int ik0 = y * TILE_KET;
+    if (ik0 >= prm.ket_n) break;
+    if (prm.same && ik0 > ib) continue;
+    if (prm.screen && prm.pair_qls[prm.bra_off + ib] + prm.pair_qls[prm.ket_off + ik0] + dlmax < prm.tlog) break;
+  }
+  const int gb = prm.bra_off + ib;
+  const int sa = prm.pair_a[gb], sb = prm.pair_b[gb];
+  const int qlb = prm.pair_ql[gb];
+  const int bra_off = prm.pair_poff[gb], bra_np = prm.pair_np[gb];
+  const double Ax = prm.sh_xyz[3 * sa], Ay = prm.sh_xyz[3 * sa + 1], Az = prm.sh_xyz[3 * sa + 2];
+  const double Bx = prm.sh_xyz[3 * sb], By = prm.sh_xyz[3 * sb + 1], Bz = prm.sh_xyz[3 * sb + 2];
+  const int fa = prm.sh_boff[sa], fb = prm.sh_boff[sb];
+  const double degab = (sa == sb) ? 1.0 : 2.0;
+  const int dab = prm.screen ? dl[sa + nsh * sb] : 0;
+  __syncthreads();  // the previous bra pair's readers of Pab / E^ab are done
+  if (MODE == 0)
+    for (int i = tid; i < NA * NB; i += 32 * NW) Pab[i] = prm.P[(fa + i % NA) + (size_t)prm.nbf * (fb + i / NA)];
+  int chunk_loaded = -1;
+
+#pragma unroll 1
+  for (int bxk = y; bxk < prm.nbx; bxk += prm.ysplit) {
+    const int ik0 = bxk * TILE_KET;
+    if (prm.same && ik0 > ib) break;
+    if (prm.screen && prm.pair_qls[gb] + prm.pair_qls[prm.ket_off + ik0] + dlmax < prm.tlog) break;
+    const int ik = ik0 + lane;
+    const bool valid = ik < prm.ket_n && (!prm.same || ik <= ib);
+    const int gk = prm.ket_off + min(ik, prm.ket_n - 1);
+    const int sc = prm.pair_a[gk], sd = prm.pair_b[gk];
+    bool active = valid;
+    if (prm.screen && valid) {
+      const int s = qlb + prm.pair_ql[gk];
+      if (s + dlmax < prm.tlog) active = false;
+      else {
+        int dm = max(dab, dl[sd + nsh * sc]);
+        dm = max(dm, max(dl[sc + nsh * sa], dl[sd + nsh * sa]));
+        dm = max(dm, max(dl[sc + nsh * sb], dl[sd + nsh * sb]));
+        active = (s + dm >= prm.tlog);
+      }
+    }
+    if (__ballot_sync(0xffffffffu, active) == 0u) continue;  // identical in every warp of the CTA
+    const int ket_off = prm.pair_poff[gk];
+    const int ket_np = prm.pair_np[gk];
+    const int kmax = __reduce_max_sync(0xffffffffu, active ? ket_np : 0);
+    if (active && w == 0) { n_q += 1u; n_pq += (unsigned)(bra_np * ket_np); }
+    const double Cx = prm.sh_xyz[3 * sc], Cy = prm.sh_xyz[3 * sc + 1], Cz = prm.sh_xyz[3 * sc + 2];
+    const double Dx = prm.sh_xyz[3 * sd], Dy = prm.sh_xyz[3 * sd + 1], Dz = prm.sh_xyz[3 * sd + 2];
+    double acc[NA * NB];
+#pragma unroll
+    for (int i = 0; i < NA * NB; ++i) acc[i] = 0.0;
+
+#pragma unroll 1
+    for (int ip0 = 0; ip0 < bra_np; ip0 += COOP_MAXBP) {
+      const int nchunk = min(COOP_MAXBP, bra_np - ip0);
+      if (chunk_loaded != ip0) {  // CTA-uniform
+        __syncthreads();
+        if (tid < 3 * nchunk) {
+          const int pi = tid / 3, axis = tid - 3 * pi;
+          const double2 *rb = prm.pp.rec + (size_t)bra_off + (size_t)(3 * TILE_KET) * (ip0 + pi);
+          const double2 b0 = __ldg(rb), b1 = __ldg(rb + TILE_KET), b2 = __ldg(rb + 2 * TILE_KET);
+          const double Pc = axis == 0 ? b0.y : (axis == 1 ? b1.x : b1.y);
+          const double Ac = axis == 0 ? Ax : (axis == 1 ? Ay : Az);
+          const double Bc = axis == 0 ? Bx : (axis == 1 ? By : Bz);
+          double E[LA + 1][LB + 1][LA + LB + 1];
+          unr::hermite_E<LA, LB, false>(E, Pc - Ac, Pc - Bc, b2.y);
+          double *dst = Es + (size_t)(pi * 3 + axis) * NE1;
+#pragma unroll
+          for (int i = 0; i <= LA; ++i)
+#pragma unroll
+            for (int j = 0; j <= LB; ++j)
+#pragma unroll
+              for (int t = 0; t <= LA + LB; ++t) dst[(i * (LB + 1) + j) * (LA + LB + 1) + t] = (t <= i + j) ? E[i][j][t] : 0.0;
+          if (axis == 0) {
+            double *br = Bs + pi * 8;
+            br[0] = b0.x; br[1] = b0.y; br[2] = b1.x; br[3] = b1.y; br[4] = b2.x;
+          }
+        }
+        chunk_loaded = ip0;
+        __syncthreads();
+      }
+#pragma unroll 1
+      for (int pi = 0; pi < nchunk; ++pi) {
+        const double p = Bs[pi * 8], Px = Bs[pi * 8 + 1], Py = Bs[pi * 8 + 2], Pz = Bs[pi * 8 + 3], kab = Bs[pi * 8 + 4];
+        const double *Ep = Es + (size_t)(pi * 3) * NE1;
+#pragma unroll 1
+        for (int iq = 0; iq < kmax; ++iq) {
+          const bool on = active && iq < ket_np;
+          const double2 *rk = prm.pp.rec + (size_t)ket_off + (size_t)(3 * TILE_KET) * min(iq, ket_np - 1);
+          const double2 k0 = __ldg(rk), k1 = __ldg(rk + TILE_KET), k2 = __ldg(rk + 2 * TILE_KET);
+          const double q = k0.x, Qx = k0.y, Qy = k1.x, Qz = k1.y;
+          const double r = rsqrt(p + q);
+          const double alpha = p * q * (r * r);
+          const double X = Px - Qx, Y = Py - Qy, Z = Pz - Qz;
+          const double T = alpha * (X * X + Y * Y + Z * Z);
+          const double pref = on ? QLB_TWO_PI_52 * kab * k2.x * r : 0.0;
+          double F[L + 1];
+          boys_array<L>(T, s_boys, F);
+          {
+            double sgn = pref;  // pref * (-2 alpha)^n
+#pragma unroll
+            for (int n = 0; n <= L; ++n) {
+              F[n] *= sgn;
+              sgn *= -2.0 * alpha;
+            }
+          }
+          build_R_columns<L, NW>(F, X, Y, Z, w, Rl);
+          __syncthreads();
+          CoopDispatch<LA, LB, LC, LD, MODE, DSEL, 0>::run(w, [&](auto icc) {
+            contract_cd<LA, LB, LC, LD, decltype(icc)::value, DSEL>(Rl, Ep, Qx - Cx, Qx - Dx, Qy - Cy, Qy - Dy, Qz - Cz, Qz - Dz,
+                                                                    k2.y, acc);
+          });
+          __syncthreads();
+        }
+      }
+    }
+    // ---- digestion / scatter of this thread's slice
+    const int fc = prm.sh_boff[sc], fd = prm.sh_boff[sd];
+    if constexpr (MODE == 0) {
+      const double deg = degab * ((sc == sd) ? 1.0 : 2.0) * ((prm.same && ib == ik) ? 1.0 : 2.0);
+      CoopDispatch<LA, LB, LC, LD, MODE, DSEL, 0>::run(w, [&](auto icc) {
+        digest_cd<LA, LB, LC, LD, decltype(icc)::value, DSEL>(acc, active, deg, fa, fb, fc, fd, Pab, prm);
+      });
+    } else {
+      if (active)
+        CoopDispatch<LA, LB, LC, LD, MODE, DSEL, 0>::run(w, [&](auto icc) {
+          scatter_cd<LA, LB, LC, LD, decltype(icc)::value, DSEL>(acc, fa, fb, fc, fd, prm);
+        });
+    }
+  }
+  }  // bra pairs
+  if (prm.counters && DSEL == 0 && w == 0) {
+    n_q = __reduce_add_sync(0xffffffffu, n_q);
+    n_pq = __reduce_add_sync(0xffffffffu, n_pq);
+    if (lane == 0 && n_q) {
+      atomicAdd(prm.counters + 0, (unsigned long long)n_q);
+      atomicAdd(prm.counters + 1, (unsigned long long)n_pq);
+    }
+  }
+}
+
+}  // namespace cop
+}  // namespace qlb

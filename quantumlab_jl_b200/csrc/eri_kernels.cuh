@@ -53,19 +53,20 @@ struct ClassParams {
   const double *__restrict__ sh_xyz;   // 3*nsh
   const int *__restrict__ sh_boff;     // first basis function of each shell
   int nsh, nbf;
-  // shell pairs (sorted by class, then Schwarz bound descending)
+  // shell pairs (sorted by class, then coarse Schwarz-bound bin descending, then shell indices: see api.cu)
   const int *__restrict__ pair_a;
   const int *__restrict__ pair_b;
   const int *__restrict__ pair_poff;   // per pair: double2 index of field 0 of its first primitive record (tile layout)
   const int *__restrict__ pair_np;     // per pair: number of primitive pairs
   const int *__restrict__ pair_ql;     // qlog(Q_ab)
+  const int *__restrict__ pair_qls;    // max of pair_ql over this and every LATER pair of the class (non-increasing: ends walks)
   PrimPairs pp;
   const double *__restrict__ boys;
   // this launch: class ranges
   int bra_off, bra_n, ket_off, ket_n, same;
   // screening
   const int *__restrict__ dl;          // nsh*nsh, qlog(max |P| over the shell block)
-  int tlog, dlmax, screen;
+  int tlog, screen;                    // the density bound max qlog|P| is read from dl[nsh*nsh] on the device
   // sharding of bra tile rows over ranks, grid decoding
   int rank, nranks, nbx;
   int ysplit;                          // CTAs per bra tile row; CTA y handles ket tiles y, y+ysplit, ...

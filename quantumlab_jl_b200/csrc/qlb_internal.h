@@ -33,6 +33,10 @@ struct Engine {
   cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {nullptr};
   double *d_boys = nullptr;
   bool profiling = false;
+  // tuning knobs, read from the environment once in qlb_init
+  int ys_target = 256, ys_tiles = 8;
+  int bin_width = 16;  // width (in qlog units, 8 per factor 2) of the Schwarz-bound bins of the pair order
+  bool ysplit_full = false, no_schedule = false;
   // NCCL (loaded lazily with dlopen)
   void *nccl_lib = nullptr;
   void *nccl_comm = nullptr;
@@ -55,7 +59,7 @@ struct qlb_basis {
   std::vector<int> h_L, h_nprim, h_poff, h_boff;
   // pairs, sorted by class then Schwarz bound (descending)
   int64_t npairs = 0;
-  std::vector<int> h_pair_a, h_pair_b, h_pair_poff, h_pair_np, h_pair_ql;
+  std::vector<int> h_pair_a, h_pair_b, h_pair_poff, h_pair_np, h_pair_ql, h_pair_qls;
   std::vector<double> h_pair_Q;
   int class_off[qlb::NCLASS + 1] = {0};
   // resolution of the identity: shells [0,n_orb) orbital, [n_orb, nsh-1) auxiliary, shell nsh-1 the unit s function;
@@ -69,7 +73,7 @@ struct qlb_basis {
   // device
   double *d_xyz = nullptr, *d_exps = nullptr, *d_coefs = nullptr;
   int *d_poff = nullptr, *d_boff = nullptr, *d_L = nullptr;
-  int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pair_poff = nullptr, *d_pair_np = nullptr, *d_pair_ql = nullptr;
+  int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pair_poff = nullptr, *d_pair_np = nullptr, *d_pair_ql = nullptr, *d_pair_qls = nullptr;
   double *d_pair_Q = nullptr;
   double2 *d_pp = nullptr;  // 3 double2 per primitive pair: {p,Px} {Py,Pz} {k/p, 1/(2p)}
   int64_t nprimpairs = 0;
@@ -80,11 +84,22 @@ struct qlb_basis {
   cudaEvent_t ev[2 * qlb::NQCLASS + 4] = {nullptr};
   // multi-rank schedule feedback: all-rank per-class counters of the previous build (summed with a second, tiny
   // all-reduce next to the [J;K] one) drive a cost model that deals whole pieces of classes to ranks
-  double *d_gcounts = nullptr;       // 2*NQCLASS doubles
-  double *h_gcounts = nullptr;       // pinned host copy
+  // [0, 2*NQCLASS): quartets / primitive quartets per class; [2*NQCLASS, 3*NQCLASS): class kernel times (ms) of the
+  // calibration build.  They travel in the tail of the [J;K] all-reduce buffer (QLB_JK_TAIL doubles): one collective.
+  double *h_gcounts = nullptr;       // pinned host copy of the all-rank sums
+  double *d_ms_local = nullptr;      // staging of this rank's class times
   cudaEvent_t ev_gcounts = nullptr;
   bool gcounts_pending = false;
   int gcounts_nranks = 0;
+  double calib_ms[qlb::NQCLASS] = {0};    // all-rank class times and work of the calibration build
+  double calib_work[qlb::NQCLASS] = {0};
+  int calib_nranks = 0;                   // 0: not calibrated
+  double h_ms_local[qlb::NQCLASS] = {0};  // this rank's class times of the calibration build, until they are reduced
+  bool ms_local_pending = false;
+  // density bound of the previous build (pinned; sizes the grids of the next build, never decides a quartet)
+  int *h_dlmax = nullptr;
+  cudaEvent_t ev_dlmax = nullptr;
+  bool dlmax_pending = false;
 };
 
 namespace qlb {

@@ -66,6 +66,8 @@ EXPORTS = (
     "qlb_comm_destroy", "qlb_allreduce_jk_device", "qlb_overlap", "qlb_kinetic", "qlb_nuclear_attraction",
     "qlb_set_profiling", "qlb_fp64_peak_probe", "qlb_ri_create", "qlb_ri_destroy", "qlb_ri_naux", "qlb_ri_b_tensor",
     "qlb_ri_eri_tensor", "qlb_ri_build_jk", "qlb_schedule_pieces", "qlb_qlog",
+    "qlb_scf_create", "qlb_scf_destroy", "qlb_scf_set_density", "qlb_scf_build", "qlb_scf_step", "qlb_scf_get",
+    "qlb_dgemm_device", "qlb_debug_set_schedule_feedback", "qlb_tensor_contract",
 )
 
 
@@ -111,6 +113,17 @@ def load():
     lib.qlb_ri_eri_tensor.argtypes = [C.c_void_p, _dp]
     lib.qlb_ri_build_jk.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
     lib.qlb_fp64_peak_probe.argtypes = [_dp]
+    if os.environ.get("QLB200_LIB") is None or hasattr(lib, "qlb_scf_create"):  # an A/B library may predate these
+        lib.qlb_scf_create.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int, C.POINTER(C.c_void_p)]
+        lib.qlb_scf_destroy.argtypes = [C.c_void_p]
+        lib.qlb_scf_set_density.argtypes = [C.c_void_p, _dp]
+        lib.qlb_scf_build.argtypes = [C.c_void_p, C.c_double, C.c_int, _dp, C.POINTER(Stats)]
+        lib.qlb_scf_step.argtypes = [C.c_void_p]
+        lib.qlb_scf_get.argtypes = [C.c_void_p, C.c_int, _dp]
+        lib.qlb_tensor_contract.argtypes = [C.c_int, _dp, _dp, C.c_int, _dp]
+        lib.qlb_debug_set_schedule_feedback.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+        lib.qlb_dgemm_device.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p]
     _lib = lib
     return lib
 

@@ -53,21 +53,18 @@ def test_product_does_not_import_oracle():
 
 
 def test_multirank_schedule_covers_every_piece_once():
-    """The feedback schedule is a pure host function: every piece of every class pair must have exactly
-    one owner, identically computed on every rank, and the modelled load must be balanced."""
+    """The measured-cost schedule is a pure host function: every piece of every class pair must have exactly
+    one owner, identically computed on every rank, and every rank must receive work."""
     import numpy as np
 
     from quantumlab_jl_b200 import libqlb
 
     lib = libqlb.load()
     rng = np.random.default_rng(0)
-    # counters shaped like the (H2O)32 build: quartets and primitive quartets per class pair
+    # measured class costs (ms) shaped like the (H2O)32 build
     for trial in range(5):
-        q = rng.integers(0, 4_000_000, 21).astype(np.float64)
-        q[rng.integers(0, 21, 3)] = 0  # some empty classes
-        gc = np.zeros(42)
-        gc[0::2] = q
-        gc[1::2] = q * rng.integers(1, 14, 21)
+        gc = rng.uniform(0.2, 8.0, 21)
+        gc[rng.integers(0, 21, 3)] = 0  # some empty classes
         for nranks in (1, 2, 3, 4, 8):
             npieces = np.zeros(21, dtype=np.int32)
             owner = np.zeros(21 * nranks, dtype=np.int32)
