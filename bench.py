@@ -41,6 +41,13 @@ WORKLOAD_DESC = {
 }
 
 
+def make_config(args, nsh, nbf, world):
+    """The SAME config dict in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "name": args.workload, "nsh": nsh, "nbf": nbf, "tau": args.tau,
+            "parallelism": f"quartet tiles sharded over {world} rank(s), 1 NCCL all-reduce of [J;K]",
+            "l2": "flushed between steps (256 MB write)", "timing": "per-step CUDA events on the launching stream, max over ranks"}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -183,23 +190,31 @@ def run_reference(args):
     rng = np.random.default_rng(0)
     A = rng.standard_normal((b.N, b.N)) * 0.05
     P = A + A.T  # the reference algorithm does not screen: its cost is independent of P
-    nthreads = os.cpu_count() or 1
+    # the reference is single-threaded: ONE host core; each step is one bounded sample of
+    # the nsh^4 quartet loop, sized so that warm-up + steps stay within ~3 minutes (>= 4 s, <= 30 s per sample)
+    nthreads = 1
+    per_step = min(30.0, max(4.0, 180.0 / max(1, args.warmup + args.steps)))
     vals, descs = [], None
     for i in range(args.warmup + args.steps):
-        v, desc, _ = cpu_reference_sample(shells, P, max(2.0, args.cpu_seconds / max(1, args.steps)), nthreads)
+        v, desc, _ = cpu_reference_sample(shells, P, per_step, nthreads)
         if i >= args.warmup:
             vals.append(v)
             descs = desc
     value = statistics.mean(vals)
+    # for context only: the same port on every host core (the reference itself cannot use them)
+    ncores = os.cpu_count() or 1
+    va, desca, _ = cpu_reference_sample(shells, P, 8.0, ncores)
+    all_cores = {"value": va, "unit": UNIT, "cores": ncores, "kind": "port", "sample": desca}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "name": args.workload, "nsh": b.nsh, "nbf": b.N},
+        "config": make_config(args, b.nsh, b.N, int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": descs},
+        "cpu_all_cores": all_cores,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference algorithm restated in C (oracle/), OpenMP over the sampled quartets; Julia is not installed here",
+        "note": "reference algorithm restated in C (oracle/), one host core like the single-threaded reference; Julia is not installed here",
     }
     print(json.dumps(line))
 
@@ -261,14 +276,16 @@ def run_ours(args):
     sptr = C.c_void_p(stream.cuda_stream)
     dP = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()  # column-major N x N == row-major transpose (P symmetric)
     dH = torch.from_numpy(np.ascontiguousarray(H.T)).cuda()
-    dJK = torch.empty(2 * N * N, dtype=torch.float64, device="cuda")
+    JK_TAIL = 64  # QLB_JK_TAIL: the schedule feedback rides behind [J;K] through the one all-reduce
+    dJK = torch.empty(2 * N * N + JK_TAIL, dtype=torch.float64, device="cuda")
     dF = torch.empty(N * N, dtype=torch.float64, device="cuda")
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # 256 MB > 126 MB L2
     h = dev.handle
     pJ, pK = C.c_void_p(dJK.data_ptr()), C.c_void_p(dJK.data_ptr() + 8 * N * N)
 
-    def step_device(stats=None):
-        libqlb.check(lib.qlb_build_jk_device(h, C.c_void_p(dP.data_ptr()), args.tau, pJ, pK, rank, world, sptr, stats))
+    def step_device(stats=None, dens=None, tau=None):
+        dens = dP if dens is None else dens
+        libqlb.check(lib.qlb_build_jk_device(h, C.c_void_p(dens.data_ptr()), args.tau if tau is None else tau, pJ, pK, rank, world, sptr, stats))
         if world > 1:
             libqlb.check(lib.qlb_allreduce_jk_device(h, C.c_void_p(dJK.data_ptr()), sptr))
         libqlb.check(lib.qlb_symmetrize_device(h, pJ, pK, sptr))
@@ -327,6 +344,35 @@ def run_ours(args):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_per_step = float(tms.item()) / args.steps
     value = 1e3 / ms_per_step
+
+    # ---- SURVEY 8(d) extras (device-timed like region 1, 3 builds each): the densities of SCF iterations 2..5 from the
+    # zero guess, and the looser threshold tau = 1e-10 on the iteration-2 density
+    def timed_builds(dens, tau, n=3):
+        step_device(dens=dens, tau=tau)  # warm-up of this density (schedule / grid guesses)
+        tot = 0.0
+        for _ in range(n):
+            flush.zero_()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            step_device(dens=dens, tau=tau)
+            b_.record(stream)
+            barrier()
+            t = torch.tensor([a.elapsed_time(b_)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot += float(t.item())
+        return tot / n
+
+    iter_ms = []
+    Pk = P
+    for k in range(2, 6):
+        dPk = torch.from_numpy(np.ascontiguousarray(np.asfortranarray(Pk).T)).cuda()
+        iter_ms.append(timed_builds(dPk, args.tau))
+        Fk = dev.fock(H, Pk)
+        _, Pk = evaluateSCFStep(Fk, S, nocc)
+    tau10_ms = timed_builds(dP, 1e-10)
+    step_device()  # leave the schedule feedback on the bench density
+    barrier()
 
     # ---- timed region 2: end to end through the host-buffer C-ABI call (pinned host buffers, copies inside)
     hP = torch.from_numpy(P.copy(order="F").reshape(-1, order="F")).pin_memory()
@@ -390,16 +436,20 @@ def run_ours(args):
             achieved = class_flops(dom, per_class[dom]["prim_quartets"], per_class[dom]["quartets"]) / (per_class[dom]["ms"] * 1e-3) * 1e-12
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))["dram_bytes_per_launch"].get(dom)
+            tr = {}
+            for fn in ("ncu_traffic_r01.json", "ncu_traffic_r02.json"):  # the newest capture wins
+                try:
+                    tr.update(json.load(open(os.path.join(ROOT, "profiles", fn)))["dram_bytes_per_launch"])
+                except (OSError, KeyError, ValueError):
+                    pass
+            traffic = tr.get(dom)
         except (OSError, KeyError, ValueError):
             pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "name": args.workload, "nsh": len(shells),
-                       "nbf": N, "tau": args.tau, "parallelism": f"quartet tiles sharded over {world} rank(s), 1 NCCL all-reduce of [J;K]",
-                       "l2": "flushed between steps (256 MB write)", "timing": "per-step CUDA events on the launching stream, max over ranks"},
+            "config": make_config(args, len(shells), N, world),
             "quartets_per_s": float(counts[0].item()) * value,
             "quartets_kept": int(counts[0].item()), "quartets_unique": stats["quartets_unique"],
             "prim_quartets": int(counts[1].item()),
@@ -410,11 +460,16 @@ def run_ours(args):
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
                          "kernel": f"eri_class_kernel {dom} (the class instantiation with the largest CUDA-event time of rank 0's build)",
-                         "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry; north_star: FP64 pipe)",
+                         "peak_source": "DFMA microbenchmark measured in this run (qlb_fp64_peak_probe: 8 independent DFMA chains per thread, "
+                                        "148 x 8 CTAs x 256 threads; MEASURED_PEAKS.json has no FP64 entry; nominal 37 TFLOP/s; north_star: FP64 pipe)",
+                         "fp64_tflops_measured": fp64_peak,
                          "all_class_kernels": {"achieved": aggregate, "frac": aggregate / fp64_peak if fp64_peak else None,
                                                "ms": eri_ms, "note": "all 21 class instantiations, serial per-class CUDA events"},
                          "algorithmic_flops_per_build": tot_flops, "hbm_gbs_measured": peaks.get("hbm_gbs"),
                          "per_class": per_class},
+            "scf_iterations_2_to_5": {"ms_per_build": [round(x, 3) for x in iter_ms], "mean_ms": sum(iter_ms) / len(iter_ms),
+                                      "note": "densities of Roothaan iterations 2..5 from the zero guess, tau as in config"},
+            "tau_1e-10": {"ms_per_build": tau10_ms, "note": "iteration-2 density, Schwarz x density threshold 1e-10"},
             "fock_symmetry_residual": check_err, "sharded_vs_single_rank_max_abs_diff": shard_err,
         }
         # CPU baselines on this box's host cores (bounded samples)

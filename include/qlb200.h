@@ -34,7 +34,8 @@ extern "C" {
 #define QLB_ERR_NCCL 4      /* collective failure                                           */
 #define QLB_ERR_NOMEM 5
 
-#define QLB_MAX_L 2         /* highest shell angular momentum with ERI class kernels (s,p,d) */
+#define QLB_MAX_L 2         /* highest ORBITAL shell angular momentum with ERI class kernels (s,p,d) */
+#define QLB_MAX_L_AUX 3     /* highest AUXILIARY (RI) shell angular momentum (s,p,d,f)           */
 #define QLB_NCLASS 6        /* shell-pair classes ss,ps,pp,ds,dp,dd                          */
 #define QLB_NQCLASS 21      /* canonical (bra class >= ket class) quartet classes            */
 #define QLB_JK_TAIL 64      /* doubles behind [J;K] that carry the schedule feedback through the one all-reduce */
@@ -59,7 +60,8 @@ typedef struct qlb_stats {
 
 /* ---- lifetime -----------------------------------------------------------------------------------------
  * replaces libint2start()/libint2stop()  (libint2jl.cpp:3-9, LibInt2Module.jl:30-40).
- * device < 0 selects the current device.  One engine per process (one process per GPU). */
+ * device < 0 selects the current device.  One engine per device; handles remember their engine, handle-less calls use the
+ * engine of the last qlb_init.  One process per GPU (torchrun) and one process driving several GPUs (qlb_multi_*) both work. */
 int qlb_init(int device);
 int qlb_finalize(void);
 const char *qlb_last_error(void);
@@ -134,27 +136,48 @@ int qlb_allreduce_jk_device(qlb_basis *b, double *dJK /* 2*N*N + QLB_JK_TAIL dou
  * p, p+np, ..); owner[qc*nranks + p] = rank that evaluates piece p.  Pure host function (tests). */
 int qlb_schedule_pieces(const double *cost, int nranks, int32_t *npieces, int32_t *owner);
 
+/* ---- single process, several GPUs: what a single Julia process (the evaluateSCF caller) uses ------------
+ * qlb_multi_create     qlb_init + qlb_basis_create on devices 0..ngpu-1 and one communicator per device (ncclCommInitAll).
+ * qlb_multi_build_jk / qlb_multi_fock: host buffers as qlb_build_jk / qlb_fock.  P (and H) go up to device 0 once and reach
+ *                      the other devices over NVLink (grouped ncclBroadcast); every device evaluates its share of the quartet
+ *                      rows of the build; ONE grouped all-reduce of [J;K]; device 0 symmetrises / assembles F and answers.
+ * qlb_multi_basis0     the device-0 qlb_basis (for qlb_overlap, qlb_schwarz, qlb_scf_create, ...). */
+typedef struct qlb_multi qlb_multi;
+int qlb_multi_create(int ngpu, int nsh, const double *centers, const int32_t *L, const int32_t *nprim, const double *exps,
+                     const double *coefs, qlb_multi **out);
+int qlb_multi_destroy(qlb_multi *m);
+int qlb_multi_ngpu(const qlb_multi *m, int *ngpu);
+int qlb_multi_basis0(qlb_multi *m, qlb_basis **b);
+int qlb_multi_build_jk(qlb_multi *m, const double *P, double tau, double *J, double *K, qlb_stats *stats);
+int qlb_multi_fock(qlb_multi *m, const double *H, const double *P, double tau, double *F, qlb_stats *stats);
+
 /* ---- one-electron matrices (SpecialMatricesModule.jl:102-177) ---------------------------- */
 int qlb_overlap(qlb_basis *b, double *S);
 int qlb_kinetic(qlb_basis *b, double *T);
 int qlb_nuclear_attraction(qlb_basis *b, int natoms, const double *xyz, const double *Z, double *V);
 
 /* ---- resolution of the identity, Coulomb metric (ResolutionIdentityModule.jl:41-78) -------------------------
- * qlb_ri_create   builds B = (mu nu|P)(P|Q)^-1/2 on the device for an auxiliary shell list (same array conventions as
- *                 qlb_basis_create): replaces computeMatrixResolutionOfTheIdentityCoulombMetric (:41-50).
- * qlb_ri_b_tensor copies B out as the reference's N x N x Naux array.
- * qlb_ri_build_jk J[mu,nu] = sum_Q B[mu,nu,Q] sum B[la,si,Q] P[la,si]  (RI-J; new) and
- *                 K[mu,la] = sum_Q sum B[mu,nu,Q] P[nu,si] B[la,si,Q]  = computeMatrixExchangeRIK (:69-78), as dense
- *                 FP64 GEMMs (cuBLAS, DMMA); the N^4 tensor of the reference is never formed.  ms (optional): device
- *                 time of the contractions. */
+ * qlb_ri_create        builds B = (mu nu|P)(P|Q)^-1/2 on the device for an auxiliary shell list (same array conventions as
+ *                      qlb_basis_create, shells up to f): replaces computeMatrixResolutionOfTheIdentityCoulombMetric
+ *                      (:41-50).  B is stored once, packed over mu >= nu; with a communicator (qlb_comm_init) every rank
+ *                      keeps a contiguous slice of the auxiliary index (qlb_ri_slice).
+ * qlb_ri_b_tensor      copies B out as the reference's N x N x Naux array (this rank's slice of Q).
+ * qlb_ri_build_jk      J[mu,nu] = sum_Q B[mu,nu,Q] sum B[la,si,Q] P[la,si]  (RI-J; new) and
+ *                      K[mu,la] = sum_Q sum B[mu,nu,Q] P[nu,si] B[la,si,Q]  = computeMatrixExchangeRIK (:69-78) for ANY
+ *                      symmetric P, with the library's own FP64 tensor-core (DMMA) GEMM and streaming GEMV kernels; the
+ *                      N^4 tensor of the reference is never formed.  The ranks' partial sums over their Q slices are
+ *                      combined by one all-reduce of [J;K].  ms (optional): device time of the contractions.
+ * qlb_ri_build_jk_occ  the same for P = Cocc Cocc^T given the occupied orbitals (N x nocc): K costs 3 N^2 nocc Naux flops. */
 typedef struct qlb_ri qlb_ri;
 int qlb_ri_create(qlb_basis *orbital, int naux_sh, const double *centers, const int32_t *L, const int32_t *nprim,
                   const double *exps, const double *coefs, qlb_ri **out);
 int qlb_ri_destroy(qlb_ri *r);
 int qlb_ri_naux(const qlb_ri *r, int *naux);
+int qlb_ri_slice(const qlb_ri *r, int *q0, int *nq);
 int qlb_ri_b_tensor(qlb_ri *r, double *B);
 int qlb_ri_eri_tensor(qlb_ri *r, double *out); /* B B^T as N^4 (computeTensorElectronRepulsionIntegralsRICoulomb :54-58), N <= 64 */
 int qlb_ri_build_jk(qlb_ri *r, const double *P, double *J, double *K, double *ms);
+int qlb_ri_build_jk_occ(qlb_ri *r, const double *Cocc, int nocc, double *J, double *K, double *ms);
 
 /* ---- SCF step on the device (HartreeFockModule.jl:73-84, :14-41; SpecialMatricesModule.jl:284-290) --------
  * A qlb_scf keeps S, T, V, P, J, K, F and the eigenvectors in HBM, so one Roothaan iteration moves four doubles to the

@@ -1,5 +1,8 @@
 # QuantumLabB200.jl -- thin Julia host side of libqlb200.so (include/qlb200.h).
 #
+# STATUS: never executed (no Julia in the build image); every name used below was checked by hand against the export /
+# import lists of the reference modules cited next to it.
+#
 # This is the binding a QuantumLab.jl maintainer adds next to LibInt2Module.jl (the reference's existing FFI seam,
 # src/SubModules/LibInt2Module.jl:30-40, 62-110, 193-334): a third shell-vector type, `B200Shells`, on which the
 # hot-path methods dispatch.  It is deliberately thin -- every line maps 1:1 onto the ctypes harness in
@@ -8,13 +11,25 @@
 module QuantumLabB200
 
 using Libdl
-using ..BaseModule, ..ShellModule, ..GeometryModule
+using LinearAlgebra
+using ..BaseModule        # Position, Ionization, LQuantumNumber (exported, BaseModule.jl:2)
+using ..ShellModule       # AbstractShell, Shell, expandShell (ShellModule.jl:2)
+using ..GeometryModule    # Geometry, computeEnergyInteratomicRepulsion, computeNumberElectrons (GeometryModule.jl:2)
+using ..BasisSetModule    # BasisSet (BasisSetModule.jl:3)
+using ..BasisModule       # computeBasisShells (BasisModule.jl:2)
+using ..InitialGuessModule  # InitialGuess, ZeroGuess, SADGuess (InitialGuessModule.jl:2)
+import ..ShellModule: nbf                                         # not exported by ShellModule (ShellModule.jl:2, :134)
+import ..InitialGuessModule: computeDensityMatrixGuess            # not exported (InitialGuessModule.jl:11-16)
+# the methods below EXTEND the reference's generic functions (new dispatch on B200Shells / B200RI), they do not shadow them
 import ..SpecialMatricesModule: computeMatrixCoulomb, computeMatrixExchange, computeMatrixFock,
-                                computeTensorElectronRepulsionIntegrals, computeTensorBlockElectronRepulsionIntegrals,
+                                computeTensorElectronRepulsionIntegrals,
                                 computeMatrixOverlap, computeMatrixKinetic, computeMatrixNuclearAttraction
+import ..IntegralsModule: computeTensorBlockElectronRepulsionIntegrals, computeElectronRepulsionIntegral
+import ..ResolutionIdentityModule: computeMatrixResolutionOfTheIdentityCoulombMetric, computeMatrixExchangeRIK,
+                                   computeTensorElectronRepulsionIntegralsRICoulomb
 import ..HartreeFockModule: evaluateSCF
 
-export B200Shells, B200RI, destroy!
+export B200Shells, B200RI, destroy!, buildJK
 
 const libqlb = Ref{Ptr{Nothing}}(C_NULL)
 
@@ -69,6 +84,7 @@ mutable struct B200Shells <: AbstractVector{Shell}
     obj
   end
 end
+B200Shells(basSet::BasisSet, geo::Geometry; kw...) = B200Shells(computeBasisShells(basSet, geo); kw...)   # BasisModule.jl:72-83
 Base.size(b::B200Shells) = size(b.shells)
 Base.getindex(b::B200Shells, i::Int) = b.shells[i]
 
@@ -141,6 +157,12 @@ function computeTensorBlockElectronRepulsionIntegrals(b::B200Shells, i::Int, j::
   blk
 end
 
+"(mu nu|la si) for components (1-based) of four shells of `b`: IntegralsModule.jl:447-462 for the functions expandShell yields."
+function computeElectronRepulsionIntegral(b::B200Shells, mu::Tuple{Int,Int}, nu::Tuple{Int,Int}, la::Tuple{Int,Int}, si::Tuple{Int,Int})
+  blk = computeTensorBlockElectronRepulsionIntegrals(b, mu[1], nu[1], la[1], si[1])
+  blk[mu[2], nu[2], la[2], si[2]]
+end
+
 # ---- resolution of the identity (ResolutionIdentityModule.jl:41-78): B stays on the device inside the handle
 mutable struct B200RI
   orbital::B200Shells
@@ -158,23 +180,90 @@ function B200RI(b::B200Shells, aux::Vector{Shell})
   B200RI(b, h[], mapreduce(nbf, +, aux))
 end
 destroy!(r::B200RI) = (ccall(dlsym(libqlb[], :qlb_ri_destroy), Cint, (Ptr{Nothing},), r.handle); r.handle = C_NULL)
+# the reference's signatures take (basis, basis_aux); these methods add the device-resident pair
 function computeMatrixResolutionOfTheIdentityCoulombMetric(r::B200RI)                                    # :41-50
-  B = Array{Float64,3}(undef, r.orbital.nbf, r.orbital.nbf, r.naux)
+  B = zeros(Float64, r.orbital.nbf, r.orbital.nbf, r.naux)
   check(ccall(dlsym(libqlb[], :qlb_ri_b_tensor), Cint, (Ptr{Nothing}, Ptr{Float64}), r.handle, B)); B
+end
+function computeMatrixResolutionOfTheIdentityCoulombMetric(b::B200Shells, aux::Vector{Shell})
+  r = B200RI(b, aux); B = computeMatrixResolutionOfTheIdentityCoulombMetric(r); destroy!(r); B
+end
+function computeTensorElectronRepulsionIntegralsRICoulomb(b::B200Shells, aux::Vector{Shell})            # :54-58 (N <= 64)
+  r = B200RI(b, aux)
+  T = Array{Float64,4}(undef, b.nbf, b.nbf, b.nbf, b.nbf)
+  check(ccall(dlsym(libqlb[], :qlb_ri_eri_tensor), Cint, (Ptr{Nothing}, Ptr{Float64}), r.handle, T)); destroy!(r); T
 end
 function computeMatrixExchangeRIK(r::B200RI, density::Matrix)                                            # :69-78
   K = Matrix{Float64}(undef, r.orbital.nbf, r.orbital.nbf)
   check(ccall(dlsym(libqlb[], :qlb_ri_build_jk), Cint, (Ptr{Nothing}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
               r.handle, Matrix{Float64}(density), C_NULL, K, C_NULL)); K
 end
+function computeMatrixExchangeRIK(b::B200Shells, aux::Vector{Shell}, density::Matrix)
+  r = B200RI(b, aux); K = computeMatrixExchangeRIK(r, density); destroy!(r); K
+end
+"RI-J and RI-K from the occupied orbital coefficients (N x nocc): the form an SCF loop uses."
+function buildJKoccRI(r::B200RI, Cocc::Matrix{Float64})
+  n = r.orbital.nbf
+  J = Matrix{Float64}(undef, n, n); K = similar(J)
+  check(ccall(dlsym(libqlb[], :qlb_ri_build_jk_occ), Cint, (Ptr{Nothing}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+              r.handle, Cocc, size(Cocc, 2), J, K, C_NULL)); J, K
+end
 
-# evaluateSCF(basis::B200Shells, geometry, guess, nocc): the convenience form (HartreeFockModule.jl:158-208) with the
-# integral-direct closures of its libint branch (:197-199,207); iteration semantics untouched.
-function evaluateSCF(b::B200Shells, geometry::Geometry, initialGuessDensity, electronNumber::Integer; kwargs...)
+# ---- evaluateSCF(basis::B200Shells, geometry, guess, electronNumber = Ionization(0); ...): the convenience form
+# (HartreeFockModule.jl:158-208) with the reference's argument types and keywords.  deviceSCF = true (default) keeps
+# S, T, V, P, J, K, F and the eigenproblem on the device (qlb_scf_*: one iteration moves four doubles to the host);
+# deviceSCF = false hands the integral-direct closures of the libint branch (:197-199, 207) to the primitive form.
+# Iteration semantics are the reference's (:104-140) in both cases.
+function evaluateSCF(b::B200Shells,
+                     geometry::Union{Geometry,String},
+                     initialGuessDensity::Union{Matrix,InitialGuess},
+                     electronNumber::Union{Integer,Ionization}=Ionization(0);
+                     detailedinfo::Bool=true, info::Bool=true, energyConvergenceCriterion::Float64=1e-8, deviceSCF::Bool=true)
+  if isa(geometry, String)
+    geometry = Geometry(geometry)
+  end
+  if isa(electronNumber, Ionization)
+    electronNumber = Int(computeNumberElectrons(geometry, electronNumber.charge) / 2)
+  end
   S = computeMatrixOverlap(b); T = computeMatrixKinetic(b); V = computeMatrixNuclearAttraction(b, geometry)
-  Pinit = InitialGuessModule.computeDensityMatrixGuess(initialGuessDensity, size(S)[1])
+  Pinit = Matrix{Float64}(computeDensityMatrixGuess(initialGuessDensity, size(S)[1]))
   Vnn = computeEnergyInteratomicRepulsion(geometry)
-  evaluateSCF(Pinit, S, T, V, P -> computeMatrixCoulomb(b, P), P -> computeMatrixExchange(b, P), Vnn, electronNumber; kwargs...)
+  if !deviceSCF
+    return evaluateSCF(Pinit, S, T, V, P -> computeMatrixCoulomb(b, P), P -> computeMatrixExchange(b, P), Vnn, electronNumber;
+                       energyConvergenceCriterion=energyConvergenceCriterion, info=info, detailedinfo=detailedinfo)
+  end
+  h = Ref{Ptr{Nothing}}(C_NULL)
+  check(ccall(dlsym(libqlb[], :qlb_scf_create), Cint, (Ptr{Nothing}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Ptr{Nothing}}),
+              b.handle, S, T, V, electronNumber, h))
+  scf = h[]
+  e4 = zeros(Float64, 4)   # 2tr(TP), 2tr(VP), 2tr(JP), -tr(KP)  (HartreeFockModule.jl:25-35)
+  build() = (check(ccall(dlsym(libqlb[], :qlb_scf_build), Cint, (Ptr{Nothing}, Cdouble, Cint, Ptr{Float64}, Ptr{Nothing}),
+                         scf, b.tau, 0, e4, C_NULL)); sum(e4))
+  try
+    check(ccall(dlsym(libqlb[], :qlb_scf_set_density), Cint, (Ptr{Nothing}, Ptr{Float64}), scf, Pinit))
+    totalEnergy = build()
+    i = 0
+    while true
+      i += 1
+      check(ccall(dlsym(libqlb[], :qlb_scf_step), Cint, (Ptr{Nothing},), scf))   # evaluateSCFStep (:73-84)
+      oldEnergy = totalEnergy
+      totalEnergy = build()
+      if info
+        println("E[$i]: $totalEnergy")
+      end
+      if abs(totalEnergy - oldEnergy) < energyConvergenceCriterion
+        info && println("Converged!")
+        break
+      end
+    end
+    n = b.nbf
+    energies = Vector{Float64}(undef, n); P = Matrix{Float64}(undef, n, n)
+    check(ccall(dlsym(libqlb[], :qlb_scf_get), Cint, (Ptr{Nothing}, Cint, Ptr{Float64}), scf, 4, energies))
+    check(ccall(dlsym(libqlb[], :qlb_scf_get), Cint, (Ptr{Nothing}, Cint, Ptr{Float64}), scf, 0, P))
+    return energies, totalEnergy, P
+  finally
+    ccall(dlsym(libqlb[], :qlb_scf_destroy), Cint, (Ptr{Nothing},), scf)
+  end
 end
 
 end # module

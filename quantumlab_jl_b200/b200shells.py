@@ -145,3 +145,55 @@ class B200Shells(list):
         else:
             raise ValueError(which)
         return out
+
+
+class B200MultiShells(list):
+    """One process, several GPUs (include/qlb200.h: qlb_multi_*): the shell-vector type a single evaluateSCF caller uses
+    to put the whole box behind `computeMatrixCoulomb/Exchange/Fock`.  Every device holds the basis; a build is sharded
+    over the devices and combined by one grouped all-reduce; device 0 answers."""
+
+    def __init__(self, shells, ngpu: int, tau: float = DEFAULT_TAU):
+        super().__init__(shells)
+        lib = libqlb.load()
+        self._arrays = flattenShells(list(self))
+        centers, L, nprim, exps, coefs = self._arrays
+        h = C.c_void_p()
+        libqlb.check(lib.qlb_multi_create(int(ngpu), len(self), libqlb.dptr(centers), libqlb.iptr(L), libqlb.iptr(nprim),
+                                          libqlb.dptr(exps), libqlb.dptr(coefs), C.byref(h)))
+        libqlb._initialised = True
+        self._h = h
+        self.ngpu = int(ngpu)
+        self.tau = float(tau)
+        self.nbf = totalBasisFunctions(list(self))
+        self.last_stats = None
+
+    def destroy(self):
+        if getattr(self, "_h", None) is not None:
+            libqlb.load().qlb_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def build_jk(self, P, tau: float | None = None):
+        P = np.asfortranarray(P, dtype=np.float64)
+        if P.shape != (self.nbf, self.nbf):
+            raise ValueError(f"density matrix must be {self.nbf}x{self.nbf}, got {P.shape}")
+        J = np.empty_like(P, order="F")
+        K = np.empty_like(P, order="F")
+        st = libqlb.Stats()
+        libqlb.check(libqlb.load().qlb_multi_build_jk(self._h, libqlb.dptr(P), self.tau if tau is None else tau, libqlb.dptr(J),
+                                                      libqlb.dptr(K), C.byref(st)))
+        self.last_stats = st.as_dict()  # device 0's share
+        return J, K
+
+    def fock(self, H, P, tau: float | None = None):
+        P = np.asfortranarray(P, dtype=np.float64)
+        H = np.asfortranarray(H, dtype=np.float64)
+        F = np.empty_like(P, order="F")
+        libqlb.check(libqlb.load().qlb_multi_fock(self._h, libqlb.dptr(H), libqlb.dptr(P), self.tau if tau is None else tau,
+                                                  libqlb.dptr(F), None))
+        return F

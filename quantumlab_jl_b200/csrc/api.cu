@@ -15,8 +15,19 @@
 namespace qlb {
 
 static thread_local std::string g_err;
-static Engine g_engine;
-Engine &engine() { return g_engine; }
+// One Engine per device.  The engine the calling thread works on follows the handle it passes in (qlb_basis carries its
+// engine); qlb_init(device) selects the engine that handle-less calls (qlb_basis_create, qlb_comm_init, ...) use.
+constexpr int MAX_DEVICES = 16;
+static Engine g_engines[MAX_DEVICES];
+static thread_local Engine *g_cur = &g_engines[0];
+#define g_engine (*g_cur)
+Engine &engine() { return *g_cur; }
+void use_engine(Engine *e) {
+  if (e && e != g_cur) {
+    g_cur = e;
+    cudaSetDevice(e->device);
+  }
+}
 void set_error(const std::string &msg) { g_err = msg; }
 int cuda_fail(cudaError_t e, const char *what) {
   set_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what);
@@ -124,6 +135,12 @@ static int require_ready() {
   return QLB_OK;
 }
 
+// entry points that receive a handle work on the handle's engine (device)
+static int enter(const qlb_basis *b) {
+  if (b && b->eng) use_engine(b->eng);
+  return require_ready();
+}
+
 template <class T>
 static int upload(T **dptr, const std::vector<T> &h) {
   QLB_CUDA(cudaMalloc((void **)dptr, std::max<size_t>(h.size(), 1) * sizeof(T)));
@@ -163,7 +180,7 @@ static void compute_pair_offsets(qlb_basis *b) {
     }
   };
   for (int c = 0; c < NCLASS; ++c) layout(b->class_off[c], b->class_off[c + 1]);
-  for (int c = 0; c < NCLASS; ++c) layout(b->ri_class_off[c], b->ri_class_off[c + 1]);
+  for (int c = 0; c < NCLASS_AUX; ++c) layout(b->ri_class_off[c], b->ri_class_off[c + 1]);
   b->h_pair_poff[b->npairs] = (int)std::min<int64_t>(slot, 0x7fffffff);
   b->nprimpairs = slot;  // double2 slots of the record buffer
 }
@@ -174,8 +191,6 @@ using namespace qlb;
 
 // =================================================================== lifetime
 extern "C" int qlb_init(int device) {
-  Engine &e = g_engine;
-  if (e.ready) return QLB_OK;
   int ndev = 0;
   cudaError_t err = cudaGetDeviceCount(&ndev);
   if (err != cudaSuccess || ndev == 0) {
@@ -184,11 +199,14 @@ extern "C" int qlb_init(int device) {
     return QLB_ERR_CUDA;
   }
   if (device < 0) QLB_CUDA(cudaGetDevice(&device));
-  if (device >= ndev) {
+  if (device >= ndev || device >= MAX_DEVICES) {
     set_error("device index out of range");
     return QLB_ERR_ARG;
   }
+  g_cur = &g_engines[device];
+  Engine &e = g_engine;
   QLB_CUDA(cudaSetDevice(device));
+  if (e.ready) return QLB_OK;
   cudaDeviceProp prop;
   QLB_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) {
@@ -220,18 +238,23 @@ extern "C" int qlb_init(int device) {
 }
 
 extern "C" int qlb_finalize(void) {
-  Engine &e = g_engine;
-  if (!e.ready) return QLB_OK;
-  qlb_comm_destroy();
-  cudaSetDevice(e.device);
-  if (e.d_boys) cudaFree(e.d_boys);
-  if (e.stream) cudaStreamDestroy(e.stream);
-  for (int i = 0; i < Engine::NSIDE; ++i) {
-    if (e.side_stream[i]) cudaStreamDestroy(e.side_stream[i]);
-    if (e.ev_join[i]) cudaEventDestroy(e.ev_join[i]);
+  Engine *keep = g_cur;
+  for (int d = 0; d < MAX_DEVICES; ++d) {
+    Engine &e = g_engines[d];
+    if (!e.ready) continue;
+    g_cur = &e;
+    cudaSetDevice(e.device);
+    qlb_comm_destroy();
+    if (e.d_boys) cudaFree(e.d_boys);
+    if (e.stream) cudaStreamDestroy(e.stream);
+    for (int i = 0; i < Engine::NSIDE; ++i) {
+      if (e.side_stream[i]) cudaStreamDestroy(e.side_stream[i]);
+      if (e.ev_join[i]) cudaEventDestroy(e.ev_join[i]);
+    }
+    if (e.ev_fork) cudaEventDestroy(e.ev_fork);
+    e = Engine();
   }
-  if (e.ev_fork) cudaEventDestroy(e.ev_fork);
-  e = Engine();
+  g_cur = keep;
   return QLB_OK;
 }
 
@@ -291,6 +314,7 @@ extern "C" int qlb_fp64_peak_probe(double *tflops) {
 // =================================================================== basis
 extern "C" int qlb_basis_destroy(qlb_basis *b) {
   if (!b) return QLB_OK;
+  if (b->eng) use_engine(b->eng);
   if (g_engine.ready) cudaSetDevice(g_engine.device);
   void *ptrs[] = {b->d_xyz, b->d_exps, b->d_coefs, b->d_poff, b->d_boff, b->d_L, b->d_pair_a, b->d_pair_b,
                   b->d_pair_poff, b->d_pair_np, b->d_pair_ql, b->d_pair_qls, b->d_pair_Q, b->d_pp,
@@ -311,7 +335,7 @@ static int basis_build_pairs(qlb_basis *b) {
   Engine &e = g_engine;
   const int nsh = b->nsh;
   // enumerate unique pairs, canonical orientation la >= lb, bucketed by class in (i,j) order
-  std::vector<int> pa[2 * NCLASS], pb[2 * NCLASS];
+  std::vector<int> pa[NCLASS + NCLASS_AUX], pb[NCLASS + NCLASS_AUX];
   const int nreg = b->n_orb > 0 ? b->n_orb : nsh;
   for (int i = 0; i < nreg; ++i)
     for (int j = 0; j <= i; ++j) {
@@ -336,7 +360,7 @@ static int basis_build_pairs(qlb_basis *b) {
     b->class_off[c + 1] = (int)b->h_pair_a.size();
   }
   b->ri_class_off[0] = (int)b->h_pair_a.size();
-  for (int c = 0; c < NCLASS; ++c) {
+  for (int c = 0; c < NCLASS_AUX; ++c) {
     b->h_pair_a.insert(b->h_pair_a.end(), pa[NCLASS + c].begin(), pa[NCLASS + c].end());
     b->h_pair_b.insert(b->h_pair_b.end(), pb[NCLASS + c].begin(), pb[NCLASS + c].end());
     b->ri_class_off[c + 1] = (int)b->h_pair_a.size();
@@ -371,11 +395,11 @@ static int basis_build_pairs(qlb_basis *b) {
   b->h_pair_Q.resize(b->npairs);
   QLB_CUDA(cudaMemcpyAsync(b->h_pair_Q.data(), b->d_pair_Q, b->npairs * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
   QLB_CUDA(cudaStreamSynchronize(e.stream));
-  // K3 (host part): order the pairs of each class by COARSE Schwarz-bound bin (descending), then by shell indices.
-  // The bins keep the early exits of the kernels (walks end where the running maximum of the bounds, pair_qls, fails),
-  // the index order inside a bin makes the 32 consecutive ket pairs of a warp neighbours in the basis: their gathers of
-  // P / dl / shell data and their J/K reductions then fall into a few cache lines instead of 32 (ncu: the light classes
-  // were bound by exactly those L1 wavefronts).  The screening DECISION per quartet does not depend on the order.
+  // K3 (host part): order the pairs of each class by quantised Schwarz bound (descending), ties by shell indices.  The
+  // walks of the kernels end where the running maximum of the bounds (pair_qls) fails.  Engine::bin_width > 1 coarsens
+  // the bound into bins and orders by shell index inside a bin (index-local tiles: fewer cache lines per gather) -- an
+  // experiment that lost on every class (mixed survivors inside a tile cost more than the gathers save), kept as a knob
+  // (QLB_BIN_W).  The screening DECISION per quartet does not depend on the order.
   std::vector<int> perm(b->npairs);
   std::iota(perm.begin(), perm.end(), 0);
   std::vector<int> ql0(b->npairs);
@@ -420,7 +444,7 @@ static int basis_build_pairs(qlb_basis *b) {
     }
   };
   for (int c = 0; c < NCLASS; ++c) suffix_max(b->class_off[c], b->class_off[c + 1]);
-  for (int c = 0; c < NCLASS; ++c) suffix_max(b->ri_class_off[c], b->ri_class_off[c + 1]);
+  for (int c = 0; c < NCLASS_AUX; ++c) suffix_max(b->ri_class_off[c], b->ri_class_off[c + 1]);
   b->h_pair_a.swap(na);
   b->h_pair_b.swap(nb);
   b->h_pair_Q.swap(nq);
@@ -458,6 +482,7 @@ int qlb::basis_create_internal(int nsh, const double *centers, const int32_t *L,
   }
   QLB_CUDA(cudaSetDevice(g_engine.device));
   qlb_basis *b = new qlb_basis();
+  b->eng = g_cur;
   b->nsh = nsh;
   b->n_orb = n_orb;
   b->h_xyz.assign(centers, centers + 3 * (size_t)nsh);
@@ -467,9 +492,12 @@ int qlb::basis_create_internal(int nsh, const double *centers, const int32_t *L,
   b->h_boff.resize(nsh + 1);
   b->h_poff[0] = b->h_boff[0] = 0;
   for (int i = 0; i < nsh; ++i) {
-    if (L[i] < 0 || L[i] > QLB_MAX_L) {
+    // orbital shells: s, p, d; auxiliary shells of an RI basis (indices >= n_orb): up to f
+    const int lmax = (n_orb > 0 && i >= n_orb) ? QLB_MAX_L_AUX : QLB_MAX_L;
+    if (L[i] < 0 || L[i] > lmax) {
       // the reference performs the analogous check against MAX_AM on the Julia side (LibInt2Module.jl:79-83)
-      set_error("qlb_basis_create: shell angular momentum outside 0..QLB_MAX_L");
+      set_error("shell " + std::to_string(i) + ": angular momentum " + std::to_string(L[i]) + " outside 0.." + std::to_string(lmax) +
+                " (QLB_MAX_L for orbital shells, QLB_MAX_L_AUX for auxiliary shells)");
       delete b;
       return QLB_ERR_ARG;
     }
@@ -537,7 +565,7 @@ extern "C" int qlb_basis_npairs(const qlb_basis *b, int64_t *npairs) {
 }
 
 extern "C" int qlb_schwarz(qlb_basis *b, double *Q) {
-  if (int rc = require_ready()) return rc;
+  if (int rc = enter(b)) return rc;
   if (!b || !Q) return QLB_ERR_ARG;
   const int n = b->nsh;
   for (int64_t i = 0; i < b->npairs; ++i) {
@@ -625,6 +653,7 @@ static double class_work(int qc, double nquart, double nprim) {
 // of a calibration build), so that one device can evaluate every piece of the scheduled deal (tests/test_gpu_parity.py).
 extern "C" int qlb_debug_set_schedule_feedback(qlb_basis *b, int nranks, const double *counts /*2*NQCLASS*/, const double *class_ms /*NQCLASS*/) {
   if (!b || !counts || !class_ms || nranks < 1) return QLB_ERR_ARG;
+  if (int rc = enter(b)) return rc;
   for (int i = 0; i < 2 * NQCLASS; ++i) b->h_gcounts[i] = counts[i];
   for (int qc = 0; qc < NQCLASS; ++qc) {
     b->calib_ms[qc] = class_ms[qc];
@@ -650,7 +679,7 @@ static int prefix_count(const qlb_basis *b, int sg, int need) {
 
 extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, double *dJ, double *dK, int rank,
                                    int nranks, void *stream_, qlb_stats *stats) {
-  if (int rc = require_ready()) return rc;
+  if (int rc = enter(b)) return rc;
   if (!b || !dP || !dJ || !dK || nranks < 1 || rank < 0 || rank >= nranks) {
     set_error("qlb_build_jk_device: bad argument");
     return QLB_ERR_ARG;
@@ -673,7 +702,9 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
   if (screen) {
     if (b->dlmax_pending) {
       QLB_CUDA(cudaEventSynchronize(b->ev_dlmax));  // recorded a whole build ago: already complete
-      dl_guess = *b->h_dlmax + 8;
+      // + one binary order of margin; never below qlog(1e-3): a build on a zero / tiny density (ZeroGuess, density
+      // differences) must not shrink the NEXT build's grids to nothing
+      dl_guess = std::max(*b->h_dlmax + 8, -80);
     }
     const int init = -32768;
     QLB_CUDA(cudaMemcpyAsync(b->d_dl + (size_t)nsh * nsh, &init, sizeof(int), cudaMemcpyHostToDevice, s));
@@ -745,11 +776,13 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       if (prm.bra_n == 0 || prm.ket_n == 0) continue;
       prm.same = (sx == sy) ? 1 : 0;
       prm.nbx = (prm.ket_n + TILE_KET - 1) / TILE_KET;
-      const int bra_sig = sig_count(sx, dl_guess);
+      // NEVER skip a launch on the strength of the guess: a class the guess finds empty still gets a minimal grid, whose
+      // CTAs either exit on the true bound or (guess too low) walk the rows with the grid stride
+      const int bra_sig = std::max(1, sig_count(sx, dl_guess));
       int ket_eff = sig_count(sy, dl_guess);
       if (screen && (int64_t)tlog - dl_guess > -40000)
         ket_eff = std::min(ket_eff, prefix_count(b, sy, tlog - dl_guess - b->h_pair_qls[b->seg_off[sx]]));
-      if (bra_sig == 0 || ket_eff == 0) continue;  // (with the margin in dl_guess; the kernels would find nothing either)
+      ket_eff = std::max(1, ket_eff);
       if (prm.same) ket_eff = std::min(ket_eff, bra_sig);
       // unscheduled: tile rows are dealt round-robin over all ranks (the rank that receives row 0, the heaviest,
       // rotates with the class pair).  scheduled: this rank owns whole pieces (row subsets p, p+np, ...) of few classes
@@ -853,7 +886,7 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
 }
 
 extern "C" int qlb_symmetrize_device(qlb_basis *b, double *dJ, double *dK, void *stream_) {
-  if (int rc = require_ready()) return rc;
+  if (int rc = enter(b)) return rc;
   if (!b) return QLB_ERR_ARG;
   cudaStream_t s = stream_ ? (cudaStream_t)stream_ : g_engine.stream;
   const int N = b->nbf;
@@ -865,7 +898,7 @@ extern "C" int qlb_symmetrize_device(qlb_basis *b, double *dJ, double *dK, void 
 }
 
 extern "C" int qlb_fock_device(qlb_basis *b, const double *dH, const double *dJ, const double *dK, double *dF, void *stream_) {
-  if (int rc = require_ready()) return rc;
+  if (int rc = enter(b)) return rc;
   if (!b || !dH || !dJ || !dK || !dF) return QLB_ERR_ARG;
   cudaStream_t s = stream_ ? (cudaStream_t)stream_ : g_engine.stream;
   const size_t n = (size_t)b->nbf * b->nbf;
@@ -889,7 +922,7 @@ static int jk_host_common(qlb_basis *b, const double *P, double tau, qlb_stats *
 }
 
 extern "C" int qlb_build_jk(qlb_basis *b, const double *P, double tau, double *J, double *K, qlb_stats *stats) {
-  if (int rc = require_ready()) return rc;
+  if (int rc = enter(b)) return rc;
   if (!b || !P || (!J && !K)) {
     set_error("qlb_build_jk: null pointer");
     return QLB_ERR_ARG;
@@ -904,7 +937,7 @@ extern "C" int qlb_build_jk(qlb_basis *b, const double *P, double tau, double *J
 }
 
 extern "C" int qlb_fock(qlb_basis *b, const double *H, const double *P, double tau, double *F, qlb_stats *stats) {
-  if (int rc = require_ready()) return rc;
+  if (int rc = enter(b)) return rc;
   if (!b || !H || !P || !F) {
     set_error("qlb_fock: null pointer");
     return QLB_ERR_ARG;
@@ -946,7 +979,7 @@ static int tensor_device(qlb_basis *b, double *dT) {
 }
 
 extern "C" int qlb_eri_tensor(qlb_basis *b, double *out) {
-  if (int rc = require_ready()) return rc;
+  if (int rc = enter(b)) return rc;
   if (!b || !out) return QLB_ERR_ARG;
   if (b->nbf > 160) {
     set_error("qlb_eri_tensor: N > 160; the N^4 tensor is only materialised for test-sized systems");
@@ -968,7 +1001,7 @@ extern "C" int qlb_eri_tensor(qlb_basis *b, double *out) {
 }
 
 extern "C" int qlb_eri_block(qlb_basis *b, int i, int j, int k, int l, double *out) {
-  if (int rc = require_ready()) return rc;
+  if (int rc = enter(b)) return rc;
   if (!b || !out) return QLB_ERR_ARG;
   const int idx[4] = {i, j, k, l};
   for (int s = 0; s < 4; ++s)
@@ -1012,15 +1045,25 @@ typedef ncclResult_t (*fn_CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
 typedef ncclResult_t (*fn_AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
 typedef ncclResult_t (*fn_CommDestroy)(ncclComm_t);
 typedef const char *(*fn_GetErrorString)(ncclResult_t);
+typedef ncclResult_t (*fn_CommInitAll)(ncclComm_t *, int, const int *);
+typedef ncclResult_t (*fn_Group)(void);
+typedef ncclResult_t (*fn_Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+void *g_nccl_lib = nullptr;
 fn_GetUniqueId p_GetUniqueId;
 fn_CommInitRank p_CommInitRank;
 fn_AllReduce p_AllReduce;
 fn_CommDestroy p_CommDestroy;
 fn_GetErrorString p_GetErrorString;
+fn_CommInitAll p_CommInitAll;
+fn_Group p_GroupStart, p_GroupEnd;
+fn_Broadcast p_Broadcast;
 
 int load_nccl() {
   Engine &e = g_engine;
-  if (e.nccl_lib) return QLB_OK;
+  if (p_AllReduce) {  // already resolved (by another device's engine)
+    if (!e.nccl_lib) e.nccl_lib = g_nccl_lib;
+    return QLB_OK;
+  }
   const char *names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char *n : names) {
     e.nccl_lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
@@ -1035,10 +1078,15 @@ int load_nccl() {
   p_AllReduce = (fn_AllReduce)dlsym(e.nccl_lib, "ncclAllReduce");
   p_CommDestroy = (fn_CommDestroy)dlsym(e.nccl_lib, "ncclCommDestroy");
   p_GetErrorString = (fn_GetErrorString)dlsym(e.nccl_lib, "ncclGetErrorString");
-  if (!p_GetUniqueId || !p_CommInitRank || !p_AllReduce || !p_CommDestroy) {
+  p_CommInitAll = (fn_CommInitAll)dlsym(e.nccl_lib, "ncclCommInitAll");
+  p_GroupStart = (fn_Group)dlsym(e.nccl_lib, "ncclGroupStart");
+  p_GroupEnd = (fn_Group)dlsym(e.nccl_lib, "ncclGroupEnd");
+  p_Broadcast = (fn_Broadcast)dlsym(e.nccl_lib, "ncclBroadcast");
+  if (!p_GetUniqueId || !p_CommInitRank || !p_AllReduce || !p_CommDestroy || !p_CommInitAll || !p_GroupStart || !p_GroupEnd || !p_Broadcast) {
     set_error("libnccl lacks a required symbol");
     return QLB_ERR_NCCL;
   }
+  g_nccl_lib = e.nccl_lib;
   return QLB_OK;
 }
 int nccl_fail(ncclResult_t r, const char *what) {
@@ -1093,8 +1141,19 @@ __global__ void jk_tail_kernel(const unsigned long long *__restrict__ c, const d
   else if (i < QLB_JK_TAIL) tail[i] = 0.0;
 }
 
+int qlb::allreduce_sum_device(double *d, size_t n, cudaStream_t s) {
+  Engine &e = g_engine;
+  if (!e.nccl_comm) {
+    set_error("allreduce: no communicator (qlb_comm_init)");
+    return QLB_ERR_STATE;
+  }
+  ncclResult_t r = p_AllReduce(d, d, n, ncclDouble, ncclSum, (ncclComm_t)e.nccl_comm, s);
+  if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce");
+  return QLB_OK;
+}
+
 extern "C" int qlb_allreduce_jk_device(qlb_basis *b, double *dJK, void *stream_) {
-  if (int rc = require_ready()) return rc;
+  if (int rc = enter(b)) return rc;
   Engine &e = g_engine;
   if (!b || !dJK) return QLB_ERR_ARG;
   if (!e.nccl_comm) {
@@ -1121,9 +1180,165 @@ extern "C" int qlb_allreduce_jk_device(qlb_basis *b, double *dJK, void *stream_)
   return QLB_OK;
 }
 
+// =================================================================== single process, several devices
+// One host thread drives ngpu devices: a qlb_basis per device, a communicator per device from ncclCommInitAll, every
+// device evaluates its share of the quartets of the SAME build, one grouped all-reduce of [J;K] combines them.  This is
+// the mode a single Julia process (the reference's evaluateSCF caller) uses to get the whole box.
+struct qlb_multi {
+  int ngpu = 0;
+  std::vector<qlb_basis *> basis;
+  std::vector<ncclComm_t> comms;
+};
+
+extern "C" int qlb_multi_destroy(qlb_multi *m) {
+  if (!m) return QLB_OK;
+  for (int d = 0; d < m->ngpu; ++d) {
+    if (d < (int)m->basis.size() && m->basis[d]) qlb_basis_destroy(m->basis[d]);
+    if (d < (int)m->comms.size() && m->comms[d]) {
+      if (p_CommDestroy) p_CommDestroy(m->comms[d]);
+      g_engines[d].nccl_comm = nullptr;
+      g_engines[d].rank = 0;
+      g_engines[d].nranks = 1;
+    }
+  }
+  delete m;
+  if (g_engines[0].ready) use_engine(&g_engines[0]);
+  return QLB_OK;
+}
+
+extern "C" int qlb_multi_create(int ngpu, int nsh, const double *centers, const int32_t *L, const int32_t *nprim, const double *exps,
+                                const double *coefs, qlb_multi **out) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device available: libqlb200 has no CPU fallback");
+    return QLB_ERR_CUDA;
+  }
+  if (!out || ngpu < 1 || ngpu > ndev || ngpu > MAX_DEVICES) {
+    set_error("qlb_multi_create: ngpu must be between 1 and the number of visible devices");
+    return QLB_ERR_ARG;
+  }
+  qlb_multi *m = new qlb_multi();
+  m->ngpu = ngpu;
+  m->basis.assign(ngpu, nullptr);
+  m->comms.assign(ngpu, nullptr);
+  for (int d = 0; d < ngpu; ++d) {
+    int rc = qlb_init(d);
+    if (!rc) rc = qlb_basis_create(nsh, centers, L, nprim, exps, coefs, &m->basis[d]);
+    if (rc) {
+      qlb_multi_destroy(m);
+      return rc;
+    }
+  }
+  if (ngpu > 1) {
+    use_engine(&g_engines[0]);
+    if (int rc = load_nccl()) {
+      qlb_multi_destroy(m);
+      return rc;
+    }
+    std::vector<int> devs(ngpu);
+    for (int d = 0; d < ngpu; ++d) devs[d] = d;
+    ncclResult_t r = p_CommInitAll(m->comms.data(), ngpu, devs.data());
+    if (r != ncclSuccess) {
+      qlb_multi_destroy(m);
+      return nccl_fail(r, "ncclCommInitAll");
+    }
+    for (int d = 0; d < ngpu; ++d) {
+      g_engines[d].nccl_comm = (void *)m->comms[d];
+      g_engines[d].rank = d;
+      g_engines[d].nranks = ngpu;
+    }
+  }
+  *out = m;
+  return QLB_OK;
+}
+
+extern "C" int qlb_multi_ngpu(const qlb_multi *m, int *ngpu) {
+  if (!m || !ngpu) return QLB_ERR_ARG;
+  *ngpu = m->ngpu;
+  return QLB_OK;
+}
+
+// P (and H) go up to device 0 once and travel to the other devices over NVLink (grouped ncclBroadcast); every device
+// enqueues its share of the build; one grouped all-reduce; device 0 symmetrises / assembles F and answers the host.
+static int multi_build(qlb_multi *m, const double *H, const double *P, double tau, double *J, double *K, double *F, qlb_stats *stats) {
+  const int n = m->ngpu;
+  qlb_basis *b0 = m->basis[0];
+  const size_t N2 = (size_t)b0->nbf * b0->nbf;
+  use_engine(&g_engines[0]);
+  QLB_CUDA(cudaMemcpyAsync(b0->d_P, P, N2 * sizeof(double), cudaMemcpyHostToDevice, g_engines[0].stream));
+  if (H) QLB_CUDA(cudaMemcpyAsync(b0->d_H, H, N2 * sizeof(double), cudaMemcpyHostToDevice, g_engines[0].stream));
+  if (n > 1) {
+    p_GroupStart();
+    for (int d = 0; d < n; ++d) {
+      use_engine(&g_engines[d]);
+      ncclResult_t r = p_Broadcast(b0->d_P, m->basis[d]->d_P, N2, ncclDouble, 0, m->comms[d], g_engines[d].stream);
+      if (r != ncclSuccess) {
+        p_GroupEnd();
+        return nccl_fail(r, "ncclBroadcast(P)");
+      }
+    }
+    ncclResult_t r = p_GroupEnd();
+    if (r != ncclSuccess) return nccl_fail(r, "ncclGroupEnd(broadcast)");
+  }
+  // the other devices first: device 0's call may wait for its stream (statistics)
+  for (int k = 0; k < n; ++k) {
+    const int d = (k + 1) % n;
+    qlb_basis *b = m->basis[d];
+    if (int rc = qlb_build_jk_device(b, b->d_P, tau, b->d_JK, b->d_JK + N2, d, n, nullptr, d == 0 ? stats : nullptr)) return rc;
+  }
+  if (n > 1) {
+    p_GroupStart();
+    for (int d = 0; d < n; ++d) {
+      if (int rc = qlb_allreduce_jk_device(m->basis[d], m->basis[d]->d_JK, nullptr)) {
+        p_GroupEnd();
+        return rc;
+      }
+    }
+    ncclResult_t r = p_GroupEnd();
+    if (r != ncclSuccess) return nccl_fail(r, "ncclGroupEnd(all-reduce)");
+  }
+  use_engine(&g_engines[0]);
+  Engine &e = g_engines[0];
+  if (int rc = qlb_symmetrize_device(b0, b0->d_JK, b0->d_JK + N2, e.stream)) return rc;
+  if (F) {
+    if (int rc = qlb_fock_device(b0, b0->d_H, b0->d_JK, b0->d_JK + N2, b0->d_P, e.stream)) return rc;  // F overwrites the P scratch
+    QLB_CUDA(cudaMemcpyAsync(F, b0->d_P, N2 * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  }
+  if (J) QLB_CUDA(cudaMemcpyAsync(J, b0->d_JK, N2 * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  if (K) QLB_CUDA(cudaMemcpyAsync(K, b0->d_JK + N2, N2 * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  for (int d = n - 1; d >= 0; --d) {
+    use_engine(&g_engines[d]);
+    QLB_CUDA(cudaStreamSynchronize(g_engines[d].stream));
+  }
+  return QLB_OK;
+}
+
+extern "C" int qlb_multi_build_jk(qlb_multi *m, const double *P, double tau, double *J, double *K, qlb_stats *stats) {
+  if (!m || !P || (!J && !K)) {
+    set_error("qlb_multi_build_jk: null pointer");
+    return QLB_ERR_ARG;
+  }
+  return multi_build(m, nullptr, P, tau, J, K, nullptr, stats);
+}
+
+extern "C" int qlb_multi_fock(qlb_multi *m, const double *H, const double *P, double tau, double *F, qlb_stats *stats) {
+  if (!m || !H || !P || !F) {
+    set_error("qlb_multi_fock: null pointer");
+    return QLB_ERR_ARG;
+  }
+  return multi_build(m, H, P, tau, nullptr, nullptr, F, stats);
+}
+
+// the device-0 handle of a multi-device object: one-electron matrices, Schwarz bounds, ... come from it
+extern "C" int qlb_multi_basis0(qlb_multi *m, qlb_basis **b) {
+  if (!m || !b) return QLB_ERR_ARG;
+  *b = m->basis[0];
+  return QLB_OK;
+}
+
 // =================================================================== one-electron matrices
 static int one_electron_host(qlb_basis *b, int which, int natoms, const double *xyz, const double *Z, double *out) {
-  if (int rc = require_ready()) return rc;
+  if (int rc = enter(b)) return rc;
   if (!b || !out || (which == 2 && (natoms <= 0 || !xyz || !Z))) return QLB_ERR_ARG;
   Engine &e = g_engine;
   QLB_CUDA(cudaSetDevice(e.device));

@@ -25,6 +25,14 @@ int launch_qc_2211(int mode, unsigned grid, cudaStream_t s, const ClassParams &p
 int launch_qc_2220(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
 int launch_qc_2221(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
 int launch_qc_2222(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+// (auxiliary f shell, unit s) pairs of the RI path: bra class 6 = (fs); rolled MODE-2 kernels only
+int launch_qc_3000(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_3010(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_3011(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_3020(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_3021(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_3022(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
+int launch_qc_3030(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm);
 
 int launch_class_kernel(int X, int Y, int mode, unsigned grid, cudaStream_t s, const ClassParams &prm) {
   switch (qclass_of(X, Y)) {
@@ -49,6 +57,13 @@ int launch_class_kernel(int X, int Y, int mode, unsigned grid, cudaStream_t s, c
     case 18: return launch_qc_2220(mode, grid, s, prm);  // (dd|ds)
     case 19: return launch_qc_2221(mode, grid, s, prm);  // (dd|dp)
     case 20: return launch_qc_2222(mode, grid, s, prm);  // (dd|dd)
+    case 21: return launch_qc_3000(mode, grid, s, prm);  // (fs|ss)  -- RI only from here
+    case 22: return launch_qc_3010(mode, grid, s, prm);  // (fs|ps)
+    case 23: return launch_qc_3011(mode, grid, s, prm);  // (fs|pp)
+    case 24: return launch_qc_3020(mode, grid, s, prm);  // (fs|ds)
+    case 25: return launch_qc_3021(mode, grid, s, prm);  // (fs|dp)
+    case 26: return launch_qc_3022(mode, grid, s, prm);  // (fs|dd)
+    case 27: return launch_qc_3030(mode, grid, s, prm);  // (fs|fs)
   }
   return (int)cudaErrorInvalidValue;
 }

@@ -6,9 +6,11 @@
 //                                           2 cooperative (eri_coop.cuh): ncart(LC) threads per quartet, R_tuv in shared memory
 //   -DQC_DSTEP=n                          ket-d components accumulated per pass (ncart(LD) = single pass)
 //   -DQC_MINB=n                           minimum resident CTAs per SM (register cap)
+//   -DQC_CPT=n                            cooperative flavour: ket-c components per thread (warps per CTA = ncart(LC)/n)
 //   -DQC_SPLIT=0|1                        1: the class is ncart(LD) launches, one per ket-d component, each compiled in
 //                                         its own TU (this file again with -DQC_DSEL=k)
 // so that the classes build in parallel and each one's policy is a Makefile entry (see DESIGN.md "K4").
+//   -DQC_RIONLY=1                         classes that only occur on the RI path (an auxiliary f shell in the bra): mode 2 only
 // mode 2 (resolution-of-the-identity scatter) always runs the rolled flavour.
 // mode -1 is a query: returns (bra pairs per CTA) | (kernel launches per class launch) << 8 without launching.
 #include "qlb_internal.h"
@@ -27,16 +29,22 @@
 
 namespace qlb {
 
+#ifndef QC_CPT
+#define QC_CPT 1
+#endif
 #if QC_UNR == 2
-template <int MODE, int DSEL>
+// one kernel serves the J/K build (mode 0) and the tensor scatter (mode 1: prm.tensor set by the caller)
+template <int DSEL>
 static int launch_coop(unsigned grid, cudaStream_t s, const ClassParams &prm) {
-  using S = cop::CoopShape<QC_LA, QC_LB, QC_LC, QC_LD>;
-  auto kern = cop::eri_coop_kernel<QC_LA, QC_LB, QC_LC, QC_LD, MODE, DSEL, QC_MINB>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  using S = cop::CoopShape<QC_LA, QC_LB, QC_LC, QC_LD, QC_CPT>;
+  auto kern = cop::eri_coop_kernel<QC_LA, QC_LB, QC_LC, QC_LD, DSEL, QC_CPT, QC_MINB>;
+  static unsigned attr_set = 0;  // one bit per device: the attribute belongs to the device's copy of the kernel
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_set >> dev) & 1u)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_set |= 1u << dev;
   }
   kern<<<grid, dim3(32, S::NW), S::SMEM_BYTES, s>>>(prm);
   return (int)cudaGetLastError();
@@ -47,7 +55,7 @@ static int launch_coop(unsigned grid, cudaStream_t s, const ClassParams &prm) {
 // ---- one ket-d component of a split class
 int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, QC_DSEL)(int mode, unsigned grid, cudaStream_t s, const ClassParams &prm) {
 #if QC_UNR == 2
-  return mode == 0 ? launch_coop<0, QC_DSEL>(grid, s, prm) : launch_coop<1, QC_DSEL>(grid, s, prm);
+  return launch_coop<QC_DSEL>(grid, s, prm);
 #else
   const dim3 block(TILE_KET, TILE_BRA);
 #if QC_UNR
@@ -81,7 +89,9 @@ int QC_CAT(QC_LA, QC_LB, QC_LC, QC_LD)(int mode, unsigned grid, cudaStream_t s, 
     return tile_bra | (nlaunch << 8);
   }
   if (mode == 0 || mode == 1) {
-#if QC_SPLIT
+#if defined(QC_RIONLY) && QC_RIONLY
+    return (int)cudaErrorInvalidValue;  // no J/K or tensor kernel exists for this class
+#elif QC_SPLIT
     int rc = QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 0)(mode, grid, s, prm);
     if (!rc) rc = QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 1)(mode, grid, s, prm);
     if (!rc) rc = QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, 2)(mode, grid, s, prm);
@@ -92,7 +102,7 @@ int QC_CAT(QC_LA, QC_LB, QC_LC, QC_LD)(int mode, unsigned grid, cudaStream_t s, 
 #endif
     return rc;
 #elif QC_UNR == 2
-    return mode == 0 ? launch_coop<0, 0>(grid, s, prm) : launch_coop<1, 0>(grid, s, prm);
+    return launch_coop<0>(grid, s, prm);
 #elif QC_UNR
     if (mode == 0) unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, QC_DSTEP, -1, QC_MINB><<<grid, block, 0, s>>>(prm);
     else unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, QC_DSTEP, -1, QC_MINB><<<grid, block, 0, s>>>(prm);

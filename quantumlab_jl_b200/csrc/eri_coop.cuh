@@ -2,9 +2,10 @@
 // (total L >= 5) whose Hermite Coulomb integrals R_tuv (56..165 doubles per primitive quartet) do not fit the register
 // file next to the accumulators.
 //
-// Several threads per shell quartet: a CTA is ONE bra shell pair x 32 ket shell pairs (the lanes) x NW = ncart(LC)
-// warps; warp w owns ket-c Cartesian component w, the launch (template parameter DSEL) owns ket-d component DSEL, so a
-// thread accumulates the NA*NB integrals (a b | c_w d_DSEL) of its lane's quartet in registers.  Per primitive quartet
+// Several threads per shell quartet: a CTA is ONE bra shell pair x 32 ket shell pairs (the lanes) x NW = ncart(LC)/CPT
+// warps; warp w owns the ket-c Cartesian components w, w+NW, .. (CPT of them), the launch (template parameter DSEL) owns
+// ket-d component DSEL, so a thread accumulates CPT*NA*NB integrals (a b | c d_DSEL) of its lane's quartet in registers.
+// Per primitive quartet
 //   1. every warp evaluates the Boys function and the one-index recursion R^n_{00v} for its lane (redundant, cheap),
 //      then builds the (u,v) columns of R_tuv dealt to it entirely in registers and parks them in SHARED memory
 //      (layout [t u v][lane]: conflict-free);
@@ -12,8 +13,11 @@
 //      memory load per R element, "scatter form") into G_tuv, then with the bra coefficients E^ab, which are CTA-uniform
 //      and sit in shared memory (broadcast loads), into the accumulators.
 // The bra-side Hermite coefficients are built once per CTA (one thread per bra primitive and axis).
-// Digestion: J_ab is reduced over the 32 lanes with a transposing shuffle tree (31 exchanges for 32 values), the
-// ket-indexed updates go out as FP64 reductions (RED) as in the register flavour.
+// Digestion: the ket-indexed updates go out as FP64 reductions (RED) as in the register flavour; the J_ab contributions
+// of the CTA's threads are first summed over the warps (the ket-c components) through shared memory, then over the 32
+// lanes with one shuffle tree per element -- per CTA, not per thread (ncu / SASS: a per-thread lane reduction of NA*NB
+// values cost more instructions than the integrals of a K = 1 quartet).
+// The same kernel serves the J/K build (prm.tensor == nullptr) and the N^4 tensor scatter of the parity tests.
 //
 // Replaces, like the other flavours, computeElectronRepulsionIntegral (IntegralsModule.jl:412-462) per quartet and
 // contractTensorBlocksWithMatrix_* (SpecialMatricesModule.jl:33-100).
@@ -76,9 +80,10 @@ __device__ __forceinline__ void static_for(F &&f) {
   static_for_impl(f, std::make_integer_sequence<int, N>());
 }
 
-template <int LA, int LB, int LC, int LD>
+template <int LA, int LB, int LC, int LD, int CPT = 1>
 struct CoopShape {
-  static constexpr int NW = ncart(LC);
+  static_assert(ncart(LC) % CPT == 0, "CPT must divide the number of ket-c components");
+  static constexpr int NW = ncart(LC) / CPT;
   static constexpr int L = LA + LB + LC + LD, LAB = LA + LB, LCD = LC + LD;
   static constexpr int NA = ncart(LA), NB = ncart(LB);
   static constexpr int NE1 = (LA + 1) * (LB + 1) * (LAB + 1);  // E^ab entries per axis
@@ -86,7 +91,9 @@ struct CoopShape {
   static constexpr int E_DOUBLES = COOP_MAXBP * 3 * NE1;
   static constexpr int B_DOUBLES = COOP_MAXBP * 8;
   static constexpr int P_DOUBLES = NA * NB;
-  static constexpr size_t SMEM_BYTES = sizeof(double) * (R_DOUBLES + E_DOUBLES + B_DOUBLES + P_DOUBLES);
+  static constexpr int JC = (NA * NB < 18) ? NA * NB : 18;  // J_ab elements reduced across the warps per round
+  static constexpr int J_DOUBLES = NW * JC * 32;
+  static constexpr size_t SMEM_BYTES = sizeof(double) * (R_DOUBLES + E_DOUBLES + B_DOUBLES + P_DOUBLES + J_DOUBLES);
 };
 
 // ---- R_tuv columns.  S1[n][v] = R^n_{0,0,v}; column (u,v): R^0_{t,u,v}, t = 0..L-u-v, built from the v-th
@@ -241,171 +248,112 @@ __device__ __forceinline__ void contract_cd(const double *__restrict__ Rl, const
   });
 }
 
-// sum v[i] over the 32 lanes for i = 0..31 with a transposing tree: afterwards lane l holds the total of v[l].
-// 16+8+4+2+1 = 31 exchanges instead of 32*5.
-__device__ __forceinline__ double transpose_reduce32(double (&v)[32], int lane) {
-#pragma unroll
-  for (int h = 16; h >= 1; h >>= 1) {
-    const bool up = (lane & h) != 0;
-#pragma unroll
-    for (int i = 0; i < h; ++i) {
-      // lanes with bit h keep the upper half v[i+h], the others the lower half v[i]; the partner's copy is added
-      const double send = up ? v[i] : v[i + h];
-      const double keep = up ? v[i + h] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-    }
-  }
-  return v[0];
-}
-// index of the value lane l ends up with after transpose_reduce32: bit h of the lane selected the upper half at step h
-__device__ __forceinline__ int transpose_reduce32_index(int lane) { return lane; }
-
-// ---- J/K digestion of one thread's (c_IC, d_ID) slice
+// ---- J/K digestion of one thread's (c_IC, d_ID) slice: the ket-indexed updates leave as reductions, the J_ab
+// contribution I*P_cd is ADDED to tab[] (reduced over warps and lanes by the caller)
 template <int LA, int LB, int LC, int LD, int IC, int ID>
 __device__ __forceinline__ void digest_cd(const double *acc, bool active, double deg, int fa, int fb, int fc, int fd,
-                                          const double *__restrict__ Pab, const ClassParams &prm) {
-  using S = CoopShape<LA, LB, LC, LD>;
-  constexpr int NA = S::NA, NB = S::NB;
+                                          const double *__restrict__ Pab, const ClassParams &prm, double *tab) {
+  constexpr int NA = ncart(LA), NB = ncart(LB);
   constexpr int cx = cart_x(LC, IC), cy = cart_y(LC, IC), dx = cart_x(LD, ID), dy = cart_y(LD, ID);
+  if (!active) return;  // (warp-divergent; no collective below)
   const int N = prm.nbf;
-  const int lane = threadIdx.x;
   const double *__restrict__ P = prm.P;
   const int gc = fc + IC, gd = fd + ID;
-  // scaled integrals (non-axial factors, degeneracy); inactive lanes carry zeros
-  const double ncd = active ? nonaxial(LC, cx, cy, LC - cx - cy) * nonaxial(LD, dx, dy, LD - dx - dy) * deg : 0.0;
-  double I[NA * NB];
-  {
-    int ib = 0;
+  const double ncd = nonaxial(LC, cx, cy, LC - cx - cy) * nonaxial(LD, dx, dy, LD - dx - dy) * deg;
+  const double pcd = __ldg(P + gc + (size_t)N * gd);
+  double jcd = 0.0;
+  double Kac[NA], Kad[NA], Kbc[NB], Kbd[NB];
 #pragma unroll
-    for (int bx = LB; bx >= 0; --bx)
+  for (int i = 0; i < NA; ++i) Kac[i] = Kad[i] = 0.0;
 #pragma unroll
-      for (int by = LB - bx; by >= 0; --by, ++ib) {
-        const double nb = nonaxial(LB, bx, by, LB - bx - by) * ncd;
-        int ia = 0;
+  for (int i = 0; i < NB; ++i) Kbc[i] = Kbd[i] = 0.0;
+  double pad[NA], pac[NA];
 #pragma unroll
-        for (int ax = LA; ax >= 0; --ax)
-#pragma unroll
-          for (int ay = LA - ax; ay >= 0; --ay, ++ia) I[ia + NA * ib] = acc[ia + NA * ib] * (nonaxial(LA, ax, ay, LA - ax - ay) * nb);
-      }
+  for (int ia = 0; ia < NA; ++ia) {
+    pad[ia] = __ldg(P + gd + (size_t)N * (fa + ia));
+    pac[ia] = __ldg(P + gc + (size_t)N * (fa + ia));
   }
-  if (active) {
-    const double pcd = __ldg(P + gc + (size_t)N * gd);
-    double jcd = 0.0;
-    double Kac[NA], Kad[NA], Kbc[NB], Kbd[NB];
+  static_for<NB>([&](auto ibc) {
+    constexpr int ib = decltype(ibc)::value;
+    constexpr int bx = cart_x(LB, ib), by = cart_y(LB, ib);
+    const double nb = nonaxial(LB, bx, by, LB - bx - by) * ncd;
+    const double pbd = __ldg(P + gd + (size_t)N * (fb + ib));
+    const double pbc = __ldg(P + gc + (size_t)N * (fb + ib));
+    static_for<NA>([&](auto iac) {
+      constexpr int ia = decltype(iac)::value;
+      constexpr int ax = cart_x(LA, ia), ay = cart_y(LA, ia);
+      const double v = acc[ia + NA * ib] * (nonaxial(LA, ax, ay, LA - ax - ay) * nb);
+      jcd = fma(v, Pab[ia + NA * ib], jcd);
+      Kac[ia] = fma(v, pbd, Kac[ia]);
+      Kad[ia] = fma(v, pbc, Kad[ia]);
+      Kbc[ib] = fma(v, pad[ia], Kbc[ib]);
+      Kbd[ib] = fma(v, pac[ia], Kbd[ib]);
+      tab[ia + NA * ib] = fma(v, pcd, tab[ia + NA * ib]);
+    });
+  });
+  atomicAdd(prm.J + gc + (size_t)N * gd, 0.5 * jcd);
 #pragma unroll
-    for (int i = 0; i < NA; ++i) Kac[i] = Kad[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < NB; ++i) Kbc[i] = Kbd[i] = 0.0;
-    double pad[NA], pac[NA];
-#pragma unroll
-    for (int ia = 0; ia < NA; ++ia) {
-      pad[ia] = __ldg(P + gd + (size_t)N * (fa + ia));
-      pac[ia] = __ldg(P + gc + (size_t)N * (fa + ia));
-    }
-#pragma unroll
-    for (int ib = 0; ib < NB; ++ib) {
-      const double pbd = __ldg(P + gd + (size_t)N * (fb + ib));
-      const double pbc = __ldg(P + gc + (size_t)N * (fb + ib));
-#pragma unroll
-      for (int ia = 0; ia < NA; ++ia) {
-        const double v = I[ia + NA * ib];
-        jcd = fma(v, Pab[ia + NA * ib], jcd);
-        Kac[ia] = fma(v, pbd, Kac[ia]);
-        Kad[ia] = fma(v, pbc, Kad[ia]);
-        Kbc[ib] = fma(v, pad[ia], Kbc[ib]);
-        Kbd[ib] = fma(v, pac[ia], Kbd[ib]);
-      }
-    }
-    atomicAdd(prm.J + gc + (size_t)N * gd, 0.5 * jcd);
-#pragma unroll
-    for (int i = 0; i < NA; ++i) {
-      atomicAdd(prm.K + gc + (size_t)N * (fa + i), 0.25 * Kac[i]);
-      atomicAdd(prm.K + gd + (size_t)N * (fa + i), 0.25 * Kad[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-      atomicAdd(prm.K + gc + (size_t)N * (fb + i), 0.25 * Kbc[i]);
-      atomicAdd(prm.K + gd + (size_t)N * (fb + i), 0.25 * Kbd[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < NA * NB; ++i) I[i] *= pcd;  // J_ab contribution of this (c,d)
+  for (int i = 0; i < NA; ++i) {
+    atomicAdd(prm.K + gc + (size_t)N * (fa + i), 0.25 * Kac[i]);
+    atomicAdd(prm.K + gd + (size_t)N * (fa + i), 0.25 * Kad[i]);
   }
-  // J_ab += sum over the 32 kets: transposing reduction in chunks of 32 values, then one RED per value
 #pragma unroll
-  for (int c0 = 0; c0 < NA * NB; c0 += 32) {
-    double v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (c0 + i < NA * NB) ? I[(c0 + i < NA * NB) ? c0 + i : 0] : 0.0;
-    if (NA * NB - c0 >= 8) {
-      const double tot = transpose_reduce32(v, lane);
-      const int i = c0 + lane;
-      if (i < NA * NB && tot != 0.0) atomicAdd(prm.J + (fa + i % NA) + (size_t)N * (fb + i / NA), 0.5 * tot);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (c0 + i >= NA * NB) break;
-        const double tot = warp_sum(v[i]);
-        if (lane == 0 && tot != 0.0) atomicAdd(prm.J + (fa + (c0 + i) % NA) + (size_t)N * (fb + (c0 + i) / NA), 0.5 * tot);
-      }
-    }
+  for (int i = 0; i < NB; ++i) {
+    atomicAdd(prm.K + gc + (size_t)N * (fb + i), 0.25 * Kbc[i]);
+    atomicAdd(prm.K + gd + (size_t)N * (fb + i), 0.25 * Kbd[i]);
   }
 }
 
-// ---- MODE 1: one thread's (c,d) slice into the N^4 tensor at its 8 symmetric positions
+// ---- tensor mode: one thread's (c,d) slice into the N^4 tensor at its 8 symmetric positions
 template <int LA, int LB, int LC, int LD, int IC, int ID>
 __device__ __forceinline__ void scatter_cd(const double *acc, int fa, int fb, int fc, int fd, const ClassParams &prm) {
-  using S = CoopShape<LA, LB, LC, LD>;
-  constexpr int NA = S::NA;
+  constexpr int NA = ncart(LA), NB = ncart(LB);
   constexpr int cx = cart_x(LC, IC), cy = cart_y(LC, IC), dx = cart_x(LD, ID), dy = cart_y(LD, ID);
   const size_t N = prm.nbf;
   double *T = prm.tensor;
   const double ncd = nonaxial(LC, cx, cy, LC - cx - cy) * nonaxial(LD, dx, dy, LD - dx - dy);
   const size_t c = fc + IC, d = fd + ID;
-  int ib = 0;
-#pragma unroll
-  for (int bx = LB; bx >= 0; --bx)
-#pragma unroll
-    for (int by = LB - bx; by >= 0; --by, ++ib) {
-      const double nb = nonaxial(LB, bx, by, LB - bx - by) * ncd;
-      int ia = 0;
-#pragma unroll
-      for (int ax = LA; ax >= 0; --ax)
-#pragma unroll
-        for (int ay = LA - ax; ay >= 0; --ay, ++ia) {
-          const double I = acc[ia + NA * ib] * (nonaxial(LA, ax, ay, LA - ax - ay) * nb);
-          const size_t a = fa + ia, b = fb + ib;
-          T[a + N * (b + N * (c + N * d))] = I;
-          T[b + N * (a + N * (c + N * d))] = I;
-          T[a + N * (b + N * (d + N * c))] = I;
-          T[b + N * (a + N * (d + N * c))] = I;
-          T[c + N * (d + N * (a + N * b))] = I;
-          T[d + N * (c + N * (a + N * b))] = I;
-          T[c + N * (d + N * (b + N * a))] = I;
-          T[d + N * (c + N * (b + N * a))] = I;
-        }
-    }
+  static_for<NA * NB>([&](auto abc) {
+    constexpr int iab = decltype(abc)::value, ia = iab % NA, ib = iab / NA;
+    constexpr int ax = cart_x(LA, ia), ay = cart_y(LA, ia), bx = cart_x(LB, ib), by = cart_y(LB, ib);
+    const double I = acc[iab] * (nonaxial(LA, ax, ay, LA - ax - ay) * nonaxial(LB, bx, by, LB - bx - by) * ncd);
+    const size_t a = fa + ia, b = fb + ib;
+    T[a + N * (b + N * (c + N * d))] = I;
+    T[b + N * (a + N * (c + N * d))] = I;
+    T[a + N * (b + N * (d + N * c))] = I;
+    T[b + N * (a + N * (d + N * c))] = I;
+    T[c + N * (d + N * (a + N * b))] = I;
+    T[d + N * (c + N * (a + N * b))] = I;
+    T[c + N * (d + N * (b + N * a))] = I;
+    T[d + N * (c + N * (b + N * a))] = I;
+  });
 }
 
-template <int LA, int LB, int LC, int LD, int MODE, int ID, int IC>
-struct CoopDispatch {  // warp w runs the code of ket-c component w
+// warp w runs the code of ket-c components w, w+NW, ..: f(integral_constant<IC>, integral_constant<slot>)
+template <int NC, int NW, int IC = 0>
+struct CoopDispatch {
   template <class F>
   static __device__ __forceinline__ void run(int w, F &&f) {
-    if (w == IC) f(std::integral_constant<int, IC>());
-    else if constexpr (IC + 1 < ncart(LC)) CoopDispatch<LA, LB, LC, LD, MODE, ID, IC + 1>::run(w, f);
+    if ((IC % NW) == w) f(std::integral_constant<int, IC>(), std::integral_constant<int, IC / NW>());
+    if constexpr (IC + 1 < NC) CoopDispatch<NC, NW, IC + 1>::run(w, f);
   }
 };
 
-// MODE 0: J/K digestion with screening; MODE 1: tensor scatter (no screening).  DSEL: the ket-d component of this launch.
-template <int LA, int LB, int LC, int LD, int MODE, int DSEL, int MINB>
-__global__ void __launch_bounds__(32 * ncart(LC), MINB) eri_coop_kernel(const __grid_constant__ ClassParams prm) {
-  using S = CoopShape<LA, LB, LC, LD>;
-  constexpr int NW = S::NW, L = S::L, NA = S::NA, NB = S::NB, NE1 = S::NE1;
+// prm.tensor == nullptr: J/K digestion with screening; else tensor scatter (no screening).
+// DSEL: the ket-d component of this launch; CPT: ket-c components per thread.
+template <int LA, int LB, int LC, int LD, int DSEL, int CPT, int MINB>
+__global__ void __launch_bounds__(32 * (ncart(LC) / CPT), MINB) eri_coop_kernel(const __grid_constant__ ClassParams prm) {
+  using S = CoopShape<LA, LB, LC, LD, CPT>;
+  constexpr int NW = S::NW, NC = ncart(LC), L = S::L, NA = S::NA, NB = S::NB, NAB = NA * NB, NE1 = S::NE1, JC = S::JC;
+  __shared__ int s_queue[NW][64];  // per-warp (identical) queues of surviving ket pairs
   extern __shared__ double coop_smem[];
   double *Rs = coop_smem;
   double *Es = Rs + S::R_DOUBLES;
   double *Bs = Es + S::E_DOUBLES;
   double *Pab = Bs + S::B_DOUBLES;
+  double *Js = Pab + S::P_DOUBLES;
   const int lane = threadIdx.x, w = threadIdx.y, tid = w * 32 + lane;
+  const bool tensor_mode = prm.tensor != nullptr;
   const double *s_boys = prm.boys + (size_t)L * BOYS_TABLE_DOUBLES;
   const int *__restrict__ dl = prm.dl;
   const int nsh = prm.nsh;
@@ -435,40 +383,25 @@ __global__ void __launch_bounds__(32 * ncart(LC), MINB) eri_coop_kernel(const __
   const double degab = (sa == sb) ? 1.0 : 2.0;
   const int dab = prm.screen ? dl[sa + nsh * sb] : 0;
   __syncthreads();  // the previous bra pair's readers of Pab / E^ab are done
-  if (MODE == 0)
-    for (int i = tid; i < NA * NB; i += 32 * NW) Pab[i] = prm.P[(fa + i % NA) + (size_t)prm.nbf * (fb + i / NA)];
+  if (!tensor_mode)
+    for (int i = tid; i < NAB; i += 32 * NW) Pab[i] = prm.P[(fa + i % NA) + (size_t)prm.nbf * (fb + i / NA)];
   int chunk_loaded = -1;
 
-#pragma unroll 1
-  for (int bxk = y; bxk < prm.nbx; bxk += prm.ysplit) {
-    const int ik0 = bxk * TILE_KET;
-    if (prm.same && ik0 > ib) break;
-    if (prm.screen && prm.pair_qls[gb] + prm.pair_qls[prm.ket_off + ik0] + dlmax < prm.tlog) break;
-    const int ik = ik0 + lane;
-    const bool valid = ik < prm.ket_n && (!prm.same || ik <= ib);
-    const int gk = prm.ket_off + min(ik, prm.ket_n - 1);
+  // ---- one batch of (up to 32) quartets of the CTA's bra pair: lane -> ket pair ik of the class (identical in every warp)
+  auto process = [&](const int ik, const bool active) {
+    const int gk = prm.ket_off + min(max(ik, 0), prm.ket_n - 1);
     const int sc = prm.pair_a[gk], sd = prm.pair_b[gk];
-    bool active = valid;
-    if (prm.screen && valid) {
-      const int s = qlb + prm.pair_ql[gk];
-      if (s + dlmax < prm.tlog) active = false;
-      else {
-        int dm = max(dab, dl[sd + nsh * sc]);
-        dm = max(dm, max(dl[sc + nsh * sa], dl[sd + nsh * sa]));
-        dm = max(dm, max(dl[sc + nsh * sb], dl[sd + nsh * sb]));
-        active = (s + dm >= prm.tlog);
-      }
-    }
-    if (__ballot_sync(0xffffffffu, active) == 0u) continue;  // identical in every warp of the CTA
     const int ket_off = prm.pair_poff[gk];
     const int ket_np = prm.pair_np[gk];
     const int kmax = __reduce_max_sync(0xffffffffu, active ? ket_np : 0);
     if (active && w == 0) { n_q += 1u; n_pq += (unsigned)(bra_np * ket_np); }
     const double Cx = prm.sh_xyz[3 * sc], Cy = prm.sh_xyz[3 * sc + 1], Cz = prm.sh_xyz[3 * sc + 2];
     const double Dx = prm.sh_xyz[3 * sd], Dy = prm.sh_xyz[3 * sd + 1], Dz = prm.sh_xyz[3 * sd + 2];
-    double acc[NA * NB];
+    double acc[CPT][NAB];
 #pragma unroll
-    for (int i = 0; i < NA * NB; ++i) acc[i] = 0.0;
+    for (int k = 0; k < CPT; ++k)
+#pragma unroll
+      for (int i = 0; i < NAB; ++i) acc[k][i] = 0.0;
 
 #pragma unroll 1
     for (int ip0 = 0; ip0 < bra_np; ip0 += COOP_MAXBP) {
@@ -526,27 +459,96 @@ __global__ void __launch_bounds__(32 * ncart(LC), MINB) eri_coop_kernel(const __
           }
           build_R_columns<L, NW>(F, X, Y, Z, w, Rl);
           __syncthreads();
-          CoopDispatch<LA, LB, LC, LD, MODE, DSEL, 0>::run(w, [&](auto icc) {
+          CoopDispatch<NC, NW>::run(w, [&](auto icc, auto slot) {
             contract_cd<LA, LB, LC, LD, decltype(icc)::value, DSEL>(Rl, Ep, Qx - Cx, Qx - Dx, Qy - Cy, Qy - Dy, Qz - Cz, Qz - Dz,
-                                                                    k2.y, acc);
+                                                                    k2.y, acc[decltype(slot)::value]);
           });
           __syncthreads();
         }
       }
     }
-    // ---- digestion / scatter of this thread's slice
+    // ---- digestion / scatter of this thread's slices
     const int fc = prm.sh_boff[sc], fd = prm.sh_boff[sd];
-    if constexpr (MODE == 0) {
+    if (!tensor_mode) {
       const double deg = degab * ((sc == sd) ? 1.0 : 2.0) * ((prm.same && ib == ik) ? 1.0 : 2.0);
-      CoopDispatch<LA, LB, LC, LD, MODE, DSEL, 0>::run(w, [&](auto icc) {
-        digest_cd<LA, LB, LC, LD, decltype(icc)::value, DSEL>(acc, active, deg, fa, fb, fc, fd, Pab, prm);
+      double tab[NAB];  // this thread's J_ab contribution (all its ket-c components)
+#pragma unroll
+      for (int i = 0; i < NAB; ++i) tab[i] = 0.0;
+      CoopDispatch<NC, NW>::run(w, [&](auto icc, auto slot) {
+        digest_cd<LA, LB, LC, LD, decltype(icc)::value, DSEL>(acc[decltype(slot)::value], active, deg, fa, fb, fc, fd, Pab, prm, tab);
       });
-    } else {
-      if (active)
-        CoopDispatch<LA, LB, LC, LD, MODE, DSEL, 0>::run(w, [&](auto icc) {
-          scatter_cd<LA, LB, LC, LD, decltype(icc)::value, DSEL>(acc, fa, fb, fc, fd, prm);
+      // J_ab: sum over the warps through shared memory, then over the lanes; JC elements per round
+      static_for<(NAB + JC - 1) / JC>([&](auto rc) {
+        constexpr int c0 = decltype(rc)::value * JC;
+        static_for<JC>([&](auto ic) {
+          constexpr int i = decltype(ic)::value;
+          Js[(w * JC + i) * 32 + lane] = (c0 + i < NAB) ? tab[c0 + i < NAB ? c0 + i : 0] : 0.0;
         });
+        __syncthreads();
+        for (int i = w; i < JC && c0 + i < NAB; i += NW) {
+          double s = 0.0;
+#pragma unroll
+          for (int ww = 0; ww < NW; ++ww) s += Js[(ww * JC + i) * 32 + lane];
+          s = warp_sum(s);
+          const int iab = c0 + i;
+          if (lane == 0 && s != 0.0) atomicAdd(prm.J + (fa + iab % NA) + (size_t)prm.nbf * (fb + iab / NA), 0.5 * s);
+        }
+        __syncthreads();
+      });
+    } else if (active) {
+      CoopDispatch<NC, NW>::run(w, [&](auto icc, auto slot) {
+        scatter_cd<LA, LB, LC, LD, decltype(icc)::value, DSEL>(acc[decltype(slot)::value], fa, fb, fc, fd, prm);
+      });
     }
+  };
+  // Survivor compaction as in the register flavour (eri_body.inc): every warp of the CTA runs the same screening walk and
+  // keeps its own, identical copy of the queue, so all warps call process() the same number of times (it synchronises).
+  int qn = 0;
+  int *queue = s_queue[w];
+  // one loop, one call site of process() (so that it is inlined): the last trip only drains the queue
+#pragma unroll 1
+  for (int bxk = y;; bxk += prm.ysplit) {
+    const int ik0 = bxk * TILE_KET;
+    bool last = bxk >= prm.nbx || (prm.same && ik0 > ib);
+    if (!last && prm.screen && prm.pair_qls[gb] + prm.pair_qls[prm.ket_off + ik0] + dlmax < prm.tlog) last = true;
+    const int ik = ik0 + lane;
+    bool active = false;
+    if (!last) {
+      active = ik < prm.ket_n && (!prm.same || ik <= ib);
+      if (prm.screen && active) {
+        const int gk = prm.ket_off + ik;
+        const int s = qlb + prm.pair_ql[gk];
+        if (s + dlmax < prm.tlog) active = false;
+        else {
+          const int sc = prm.pair_a[gk], sd = prm.pair_b[gk];
+          int dm = max(dab, dl[sd + nsh * sc]);
+          dm = max(dm, max(dl[sc + nsh * sa], dl[sd + nsh * sa]));
+          dm = max(dm, max(dl[sc + nsh * sb], dl[sd + nsh * sb]));
+          active = (s + dm >= prm.tlog);
+        }
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, active);  // identical in every warp of the CTA
+    int ikc = ik;
+    bool act = active, run = m != 0u;
+    if (!tensor_mode) {
+      if (active) queue[qn + __popc(m & ((1u << lane) - 1u))] = ik;
+      qn += __popc(m);
+      __syncwarp();
+      run = qn >= 32 || (last && qn > 0);
+      if (run) {
+        const int take = min(qn, 32), rest = qn - take;
+        act = lane < take;
+        ikc = act ? queue[lane] : 0;
+        const int carry = (lane < rest) ? queue[32 + lane] : 0;
+        __syncwarp();
+        if (lane < rest) queue[lane] = carry;
+        qn = rest;
+        __syncwarp();
+      }
+    }
+    if (run) process(ikc, act);
+    if (last) break;
   }
   }  // bra pairs
   if (prm.counters && DSEL == 0 && w == 0) {

@@ -13,6 +13,7 @@ namespace qlb {
 
 constexpr int NCLASS = QLB_NCLASS;    // ss ps pp ds dp dd
 constexpr int NQCLASS = QLB_NQCLASS;  // X>=Y pairs of the above
+constexpr int NCLASS_AUX = 7;         // (auxiliary shell, unit s) pair classes of the RI path: ss ps . ds . . fs -> s, p, d, f shells
 inline int class_of(int la, int lb) { return la * (la + 1) / 2 + lb; }
 inline void class_L(int c, int &la, int &lb) {
   la = 0;
@@ -35,14 +36,17 @@ struct Engine {
   bool profiling = false;
   // tuning knobs, read from the environment once in qlb_init
   int ys_target = 256, ys_tiles = 8;
-  int bin_width = 16;  // width (in qlog units, 8 per factor 2) of the Schwarz-bound bins of the pair order
+  // width (in qlog units, 8 per factor 2) of the Schwarz-bound bins of the pair order; 1 = exact order of the bounds.
+  // Measured on (H2O)32: wider bins (index-local tiles) LOSE -- 45.5 / 54 / 62 / 74 / 85 ms per build for 1 / 8 / 16 / 32 / 64
+  int bin_width = 1;
   bool ysplit_full = false, no_schedule = false;
   // NCCL (loaded lazily with dlopen)
   void *nccl_lib = nullptr;
   void *nccl_comm = nullptr;
   int rank = 0, nranks = 1;
 };
-Engine &engine();
+Engine &engine();            // the engine (device) the calling thread currently works on
+void use_engine(Engine *e);  // switch to a handle's engine (and its device)
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what);
 #define QLB_CUDA(call)                                   \
@@ -54,6 +58,7 @@ int cuda_fail(cudaError_t e, const char *what);
 }  // namespace qlb
 
 struct qlb_basis {
+  qlb::Engine *eng = nullptr;  // the engine (device) that owns the device memory below
   int nsh = 0, nbf = 0, nprim_total = 0;
   std::vector<double> h_xyz, h_exps, h_coefs;
   std::vector<int> h_L, h_nprim, h_poff, h_boff;
@@ -65,7 +70,7 @@ struct qlb_basis {
   // resolution of the identity: shells [0,n_orb) orbital, [n_orb, nsh-1) auxiliary, shell nsh-1 the unit s function;
   // pair group 0 = orbital pairs (class_off), group 1 = (aux, unit) pairs (ri_class_off).  n_orb == 0: ordinary basis
   int n_orb = 0;
-  int ri_class_off[qlb::NCLASS + 1] = {0};
+  int ri_class_off[qlb::NCLASS_AUX + 1] = {0};
   // segments: each class is split by contraction degree (primitive pairs per shell pair) so that the threads of a
   // warp run primitive loops of similar length; every segment is sorted by Schwarz bound, descending
   std::vector<int> seg_off, seg_cls;
@@ -112,6 +117,8 @@ void class_flops(int X, int Y, double &f_prim, double &f_digest);
 int basis_create_internal(int nsh, const double *centers, const int32_t *L, const int32_t *nprim, const double *exps,
                           const double *coefs, int n_orb, qlb_basis **out);
 void base_class_params(qlb_basis *b, ClassParams &prm);
+// sum over the ranks of the engine's communicator, in place (api.cu; NCCL)
+int allreduce_sum_device(double *d, size_t n, cudaStream_t s);
 // one-electron kernels (one_electron.cu)
 int one_electron_device(qlb_basis *b, int which, int natoms, const double *d_xyzZ, double *d_out, cudaStream_t s);
 }  // namespace qlb

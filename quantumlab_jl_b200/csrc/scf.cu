@@ -97,6 +97,7 @@ int solver_fail(cusolverStatus_t st, const char *what) {
 
 extern "C" int qlb_scf_destroy(qlb_scf *s) {
   if (!s) return QLB_OK;
+  if (s->b && s->b->eng) use_engine(s->b->eng);
   if (engine().ready) cudaSetDevice(engine().device);
   void *ptrs[] = {s->d_S, s->d_T, s->d_V, s->d_P, s->d_F, s->d_JK, s->d_C, s->d_Swork, s->d_eps, s->d_Pbuilt, s->d_dP,
                   s->d_dJK, s->d_part, s->d_work, s->d_info};
@@ -109,6 +110,7 @@ extern "C" int qlb_scf_destroy(qlb_scf *s) {
 }
 
 extern "C" int qlb_scf_create(qlb_basis *b, const double *S, const double *T, const double *V, int nocc, qlb_scf **out) {
+  if (b && b->eng) use_engine(b->eng);
   Engine &e = engine();
   if (!e.ready) {
     set_error("qlb_init has not been called");
@@ -163,6 +165,7 @@ extern "C" int qlb_scf_create(qlb_basis *b, const double *S, const double *T, co
 
 extern "C" int qlb_scf_set_density(qlb_scf *s, const double *P) {
   if (!s || !P) return QLB_ERR_ARG;
+  use_engine(s->b->eng);
   Engine &e = engine();
   QLB_CUDA(cudaSetDevice(e.device));
   const size_t N2 = (size_t)s->N * s->N;
@@ -175,6 +178,7 @@ extern "C" int qlb_scf_set_density(qlb_scf *s, const double *P) {
 // components of HartreeFockModule.jl:25-35 for (P, J, K).  incremental != 0: J(P) = J(P_built) + J(P - P_built).
 extern "C" int qlb_scf_build(qlb_scf *s, double tau, int incremental, double *energies4, qlb_stats *stats) {
   if (!s) return QLB_ERR_ARG;
+  use_engine(s->b->eng);
   Engine &e = engine();
   if (!e.ready) return QLB_ERR_STATE;
   QLB_CUDA(cudaSetDevice(e.device));
@@ -214,6 +218,7 @@ extern "C" int qlb_scf_build(qlb_scf *s, double tau, int incremental, double *en
 // F = T + V + 2J - K; (eps, C) = eigen(F, S); P = C[:, :nocc] C[:, :nocc]^T   (HartreeFockModule.jl:73-84)
 extern "C" int qlb_scf_step(qlb_scf *s) {
   if (!s) return QLB_ERR_ARG;
+  use_engine(s->b->eng);
   Engine &e = engine();
   if (!e.ready) return QLB_ERR_STATE;
   QLB_CUDA(cudaSetDevice(e.device));
@@ -243,6 +248,7 @@ extern "C" int qlb_scf_step(qlb_scf *s) {
 // what: 0 P, 1 F, 2 J, 3 K, 4 orbital energies (N), 5 orbital coefficients C (N x N)
 extern "C" int qlb_scf_get(qlb_scf *s, int what, double *out) {
   if (!s || !out) return QLB_ERR_ARG;
+  use_engine(s->b->eng);
   Engine &e = engine();
   QLB_CUDA(cudaSetDevice(e.device));
   const size_t N2 = (size_t)s->N * s->N;

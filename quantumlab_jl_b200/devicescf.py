@@ -79,12 +79,14 @@ def evaluateSCF_device(basis: B200Shells, Pinit, S, T, V, Vnn: float, nocc: int,
     try:
         scf.set_density(Pinit)
         # the reference evaluates J and K on the initial guess (twice, :118 and :123-124); one build gives the same numbers
-        total = sum(scf.build(incremental=False))
+        total = sum(scf.build(incremental=False, want_stats=True))
+        basis.build_history.append(scf.last_stats["quartets_kept"])
         i = 0
         while True:
             i += 1
             scf.step()
-            eT, eV, eJ, eK = scf.build(incremental=incremental, want_stats=info)
+            eT, eV, eJ, eK = scf.build(incremental=incremental, want_stats=True)
+            basis.build_history.append(scf.last_stats["quartets_kept"])
             old, total = total, eT + eV + eJ + eK
             if detailedinfo:
                 print("=================================")

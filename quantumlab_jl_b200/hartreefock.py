@@ -156,7 +156,7 @@ def evaluateSCF(*args, **kw):
         Pinit = initial_density(S.shape[0])
         Vnn = computeEnergyInteratomicRepulsion(geometry)
         if kw.get("deviceSCF", True):
-            out = evaluateSCF_device(basis, Pinit, S, T, V, Vnn, electronNumber, incremental=kw.get("incremental", False), **loop)
+            out = evaluateSCF_device(basis, Pinit, S, T, V, Vnn, electronNumber, incremental=kw.get("incremental", basis.incremental), **loop)
             evaluateSCF.last_iterations = evaluateSCF_device.last_iterations
             return out
         basis.incremental = bool(kw.get("incremental", basis.incremental))

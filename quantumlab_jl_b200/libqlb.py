@@ -67,7 +67,8 @@ EXPORTS = (
     "qlb_set_profiling", "qlb_fp64_peak_probe", "qlb_ri_create", "qlb_ri_destroy", "qlb_ri_naux", "qlb_ri_b_tensor",
     "qlb_ri_eri_tensor", "qlb_ri_build_jk", "qlb_schedule_pieces", "qlb_qlog",
     "qlb_scf_create", "qlb_scf_destroy", "qlb_scf_set_density", "qlb_scf_build", "qlb_scf_step", "qlb_scf_get",
-    "qlb_dgemm_device", "qlb_debug_set_schedule_feedback", "qlb_tensor_contract",
+    "qlb_dgemm_device", "qlb_debug_set_schedule_feedback", "qlb_tensor_contract", "qlb_ri_slice", "qlb_ri_build_jk_occ",
+    "qlb_multi_create", "qlb_multi_destroy", "qlb_multi_ngpu", "qlb_multi_basis0", "qlb_multi_build_jk", "qlb_multi_fock",
 )
 
 
@@ -113,17 +114,32 @@ def load():
     lib.qlb_ri_eri_tensor.argtypes = [C.c_void_p, _dp]
     lib.qlb_ri_build_jk.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
     lib.qlb_fp64_peak_probe.argtypes = [_dp]
-    if os.environ.get("QLB200_LIB") is None or hasattr(lib, "qlb_scf_create"):  # an A/B library may predate these
-        lib.qlb_scf_create.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int, C.POINTER(C.c_void_p)]
-        lib.qlb_scf_destroy.argtypes = [C.c_void_p]
-        lib.qlb_scf_set_density.argtypes = [C.c_void_p, _dp]
-        lib.qlb_scf_build.argtypes = [C.c_void_p, C.c_double, C.c_int, _dp, C.POINTER(Stats)]
-        lib.qlb_scf_step.argtypes = [C.c_void_p]
-        lib.qlb_scf_get.argtypes = [C.c_void_p, C.c_int, _dp]
-        lib.qlb_tensor_contract.argtypes = [C.c_int, _dp, _dp, C.c_int, _dp]
-        lib.qlb_debug_set_schedule_feedback.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
-        lib.qlb_dgemm_device.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p,
-                                         C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p]
+    ab_library = os.environ.get("QLB200_LIB") is not None  # an A/B library may predate the newest entry points
+
+    def proto(name, argtypes):
+        if not hasattr(lib, name):
+            if ab_library:
+                return
+            raise QlbError(f"{LIB_PATH} lacks {name}: rebuild it (python -c 'import __graft_entry__ as g; g.build()')")
+        getattr(lib, name).argtypes = argtypes
+
+    proto("qlb_scf_create", [C.c_void_p, _dp, _dp, _dp, C.c_int, C.POINTER(C.c_void_p)])
+    proto("qlb_scf_destroy", [C.c_void_p])
+    proto("qlb_scf_set_density", [C.c_void_p, _dp])
+    proto("qlb_scf_build", [C.c_void_p, C.c_double, C.c_int, _dp, C.POINTER(Stats)])
+    proto("qlb_scf_step", [C.c_void_p])
+    proto("qlb_scf_get", [C.c_void_p, C.c_int, _dp])
+    proto("qlb_multi_create", [C.c_int, C.c_int, _dp, _ip, _ip, _dp, _dp, C.POINTER(C.c_void_p)])
+    proto("qlb_multi_destroy", [C.c_void_p])
+    proto("qlb_multi_ngpu", [C.c_void_p, _ip])
+    proto("qlb_multi_basis0", [C.c_void_p, C.POINTER(C.c_void_p)])
+    proto("qlb_multi_build_jk", [C.c_void_p, _dp, C.c_double, _dp, _dp, C.POINTER(Stats)])
+    proto("qlb_multi_fock", [C.c_void_p, _dp, _dp, C.c_double, _dp, C.POINTER(Stats)])
+    proto("qlb_ri_slice", [C.c_void_p, _ip, _ip])
+    proto("qlb_ri_build_jk_occ", [C.c_void_p, _dp, C.c_int, _dp, _dp, _dp])
+    proto("qlb_tensor_contract", [C.c_int, _dp, _dp, C.c_int, _dp])
+    proto("qlb_debug_set_schedule_feedback", [C.c_void_p, C.c_int, _dp, _dp])
+    proto("qlb_dgemm_device", [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p])
     _lib = lib
     return lib
 

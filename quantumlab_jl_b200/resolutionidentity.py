@@ -5,8 +5,10 @@ computeTensorElectronRepulsionIntegralsRICoulomb(basis, basis_aux)    -- :54-58 
 computeMatrixExchangeRIK(basis, basis_aux, density)                   -- :69-78   K without ever forming N^4
 computeMatrixCoulombRIJ(basis, basis_aux, density)                    -- new: the matching RI-J
 
-`basis` / `basis_aux` are shell lists (or a B200Shells for `basis`); the auxiliary shells go through the same
-normalisation contract as orbital shells.  B200RI keeps B on the device for repeated builds inside an SCF loop.
+`basis` / `basis_aux` are shell lists (or a B200Shells for `basis`; a GaussianBasis is regrouped into shells); the
+auxiliary shells (up to f) go through the same normalisation contract as orbital shells.  B200RI keeps B on the device
+(packed over mu >= nu, this rank's slice of the auxiliary index) for repeated builds inside an SCF loop;
+`build_jk_occ(Cocc)` is the occupied-orbital form an SCF driver uses (P = Cocc Cocc').
 """
 from __future__ import annotations
 
@@ -19,8 +21,22 @@ from .b200shells import B200Shells
 from .shell import flattenShells, totalBasisFunctions
 
 
+def _as_shell_list(basis):
+    from .basisfunctions import GaussianBasis, shells_from_functions
+
+    if isinstance(basis, GaussianBasis):
+        shells, shell_of, comp_of, scale = shells_from_functions(basis.contractedBFs)
+        from .shell import nbf
+
+        if len(basis.contractedBFs) != sum(nbf(s) for s in shells) or not np.allclose(scale, 1.0, rtol=1e-12):
+            raise ValueError("the RI path needs a GaussianBasis made of complete shells (convert(GaussianBasis, shells))")
+        return shells
+    return basis
+
+
 class B200RI:
     def __init__(self, basis, basis_aux):
+        basis, basis_aux = _as_shell_list(basis), _as_shell_list(basis_aux)
         self._own = not isinstance(basis, B200Shells)
         self.orbital = B200Shells(basis) if self._own else basis
         self._arrays = flattenShells(list(basis_aux))
@@ -47,7 +63,7 @@ class B200RI:
             pass
 
     def b_tensor(self) -> np.ndarray:
-        out = np.empty((self.nbf, self.nbf, self.naux), dtype=np.float64, order="F")
+        out = np.zeros((self.nbf, self.nbf, self.naux), dtype=np.float64, order="F")
         libqlb.check(libqlb.load().qlb_ri_b_tensor(self._h, libqlb.dptr(out)))
         return out
 
@@ -68,6 +84,24 @@ class B200RI:
                                                    libqlb.dptr(K) if want_k else None, C.byref(ms)))
         self.last_ms = ms.value
         return J, K
+
+    def build_jk_occ(self, Cocc, want_j=True, want_k=True):
+        """J and K for P = Cocc Cocc' from the occupied orbital coefficients (N x nocc)."""
+        Cm = np.asfortranarray(Cocc, dtype=np.float64)
+        if Cm.ndim != 2 or Cm.shape[0] != self.nbf:
+            raise ValueError(f"Cocc must be {self.nbf} x nocc")
+        J = np.empty((self.nbf, self.nbf), order="F") if want_j else None
+        K = np.empty((self.nbf, self.nbf), order="F") if want_k else None
+        ms = C.c_double()
+        libqlb.check(libqlb.load().qlb_ri_build_jk_occ(self._h, libqlb.dptr(Cm), Cm.shape[1], libqlb.dptr(J) if want_j else None,
+                                                       libqlb.dptr(K) if want_k else None, C.byref(ms)))
+        self.last_ms = ms.value
+        return J, K
+
+    def slice(self):
+        q0, nq = C.c_int32(), C.c_int32()
+        libqlb.check(libqlb.load().qlb_ri_slice(self._h, C.byref(q0), C.byref(nq)))
+        return q0.value, nq.value
 
 
 def _with_ri(basis, basis_aux, fn):

@@ -82,6 +82,15 @@ def build(name: str):
     return geo, shells, cfg["nocc"]
 
 
+def jkfit_aux(geo: Geometry, name: str = "jkfit-et-dz"):
+    """Auxiliary shells of config 5: the vendored JK-fitting set (an even-tempered stand-in for cc-pVDZ-JKFIT with s, p, d
+    and f shells, data/basis/jkfit-et-dz.tx93) on the atoms of `geo`."""
+    from .basisset import loadBasisSet
+    from .shell import computeBasisShells
+
+    return computeBasisShells(loadBasisSet(name), geo)
+
+
 def even_tempered_aux(geo: Geometry):
     """A synthetic auxiliary basis (the cc-pVDZ-JKFIT data cannot be vendored offline): per atom even-tempered
     uncontracted s (6), p (4) and d (3) shells -> 36 Cartesian functions per atom."""

@@ -220,3 +220,26 @@ def test_dmma_gemm_matches_numpy(qlb, ta, tb, M, N, K):
     torch.cuda.synchronize()
     got = dC.cpu().numpy().T
     assert np.abs(got - ref).max() < 1e-12 * max(1, K)
+
+
+def test_single_process_multi_gpu_matches_single_gpu(orc, qlb):
+    """qlb_multi_*: one process drives every visible GPU; the sharded + all-reduced J, K equal the one-GPU build."""
+    import torch
+
+    from quantumlab_jl_b200.b200shells import B200MultiShells, B200Shells
+
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least two GPUs")
+    geo, shells, b, nocc = make_basis(orc, "benzene_ccpvdz")
+    P = _synthetic_density(shells, seed=3)
+    one = B200Shells(shells)
+    J1, K1 = one.build_jk(P, tau=TAU)
+    multi = B200MultiShells(shells, ngpu)
+    for _ in range(3):  # calibration build, first scheduled build, steady state
+        J, K = multi.build_jk(P, tau=TAU)
+        assert np.abs(J - J1).max() < 1e-12 and np.abs(K - K1).max() < 1e-12
+    H = one.one_electron("kinetic") + one.one_electron("nuclear", geo)
+    assert np.abs(multi.fock(H, P, tau=TAU) - (H + 2 * J1 - K1)).max() < 1e-11
+    multi.destroy()
+    one.destroy()

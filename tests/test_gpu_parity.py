@@ -286,3 +286,19 @@ def test_edge_cases_tiny_ragged_and_distant(orc, qlb):
         J0, K0 = dev.build_jk(P, tau=1e30)
         assert not J0.any() and not K0.any() and dev.last_stats["quartets_kept"] == 0
         dev.destroy()
+
+
+def test_build_after_zero_density_is_complete(orc, qlb):
+    """The grids of a build are sized from the PREVIOUS build's density bound: a build on the zero density (ZeroGuess) or on a
+    tiny density must not make the next build lose quartets; and a 1000x larger density after a small one neither."""
+    geo, shells, b, _ = make_basis(orc, "h2o4_631gs")
+    dev = _b200(shells)
+    P = _rand_sym(b.N, 11, 0.3)
+    J0, K0 = dev.build_jk(P, tau=1e-12)
+    kept0 = dev.last_stats["quartets_kept"]
+    for prev in (np.zeros_like(P), 1e-9 * P, 1e3 * P):
+        dev.build_jk(prev, tau=1e-12)
+        J, K = dev.build_jk(P, tau=1e-12)
+        assert dev.last_stats["quartets_kept"] == kept0
+        assert np.abs(J - J0).max() < 1e-12 and np.abs(K - K0).max() < 1e-12
+    dev.destroy()

@@ -55,3 +55,43 @@ def test_cuda_ri_against_oracle(orc, name):
     assert np.abs(K - orc.ri_exchange(Br, P)).max() < 1e-8
     # RI with aux = orbital product space is not exact, but the diagonal (mu nu|mu nu) fit is variational: below exact
     ri.destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["h2o_631gs", "h2o2_631gs"])
+def test_cuda_ri_jkfit_aux_with_f_shells(orc, name):
+    """A JK-fitting auxiliary basis with f shells (data/basis/jkfit-et-dz.tx93): B against the oracle's numpy RI, the
+    general-P and the occupied-orbital contractions against each other and the oracle, the fit against the exact J/K."""
+    from quantumlab_jl_b200 import workloads
+    from quantumlab_jl_b200.b200shells import B200Shells
+    from quantumlab_jl_b200.hartreefock import evaluateSCFStep
+    from quantumlab_jl_b200.resolutionidentity import B200RI
+    from quantumlab_jl_b200.shell import flattenShells
+
+    geo, shells, b, nocc = make_basis(orc, name)
+    aux = workloads.jkfit_aux(geo)
+    assert max(s.lqn.exponent for s in aux) == 3
+    baux = orc.Basis(*flattenShells(aux))
+    dev = B200Shells(shells)
+    ri = B200RI(dev, aux)
+    assert ri.slice() == (0, baux.N)
+    Br = orc.ri_b_tensor(b, baux)
+    B = ri.b_tensor()
+    T, Tr = np.einsum("mnq,lsq->mnls", B, B), np.einsum("mnq,lsq->mnls", Br, Br)
+    assert np.abs(T - Tr).max() < 1e-8
+    S = dev.one_electron("overlap"); H = dev.one_electron("kinetic") + dev.one_electron("nuclear", geo)
+    import scipy.linalg
+
+    w, v = scipy.linalg.eigh(H, S)
+    Cocc = np.asfortranarray(v[:, :nocc])
+    P = Cocc @ Cocc.T
+    J, K = ri.build_jk(P)
+    Jo, Ko = ri.build_jk_occ(Cocc)
+    assert np.abs(J - orc.ri_coulomb(Br, P)).max() < 1e-8 and np.abs(K - orc.ri_exchange(Br, P)).max() < 1e-8
+    assert np.abs(Jo - J).max() < 1e-10 and np.abs(Ko - K).max() < 1e-10
+    assert np.array_equal(Ko, Ko.T)
+    # quality of the stand-in auxiliary basis: RI-J/K energies within 1e-3 relative of the exact ones
+    Jx, Kx = dev.build_jk(P, tau=0.0)
+    assert abs(np.trace(J @ P) / np.trace(Jx @ P) - 1) < 1e-3 and abs(np.trace(K @ P) / np.trace(Kx @ P) - 1) < 1e-3
+    ri.destroy()
+    dev.destroy()
