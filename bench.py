@@ -38,6 +38,10 @@ WORKLOAD_DESC = {
     "h2o64_ccpvdz": "(H2O)_64 cc-pVDZ RHF conventional Fock build (N=1600)",
     "c40h82_def2svp": "C40H82 def2-SVP RHF Fock build (N=1010)",
     "h2o4_631gs": "(H2O)_4 6-31G* (smoke size)",
+    "h2o64_ccpvdz_rijk": "(H2O)_64 cc-pVDZ RI-JK Fock build (N=1600), JK-fitting auxiliary basis with s,p,d,f shells "
+                         "(jkfit-et-dz: even-tempered stand-in for cc-pVDZ-JKFIT, Naux=7040), occupied-orbital RI-K",
+    "h2o32_631gs_rijk": "(H2O)_32 6-31G* RI-JK Fock build (N=608), jkfit-et-dz auxiliary basis (Naux=3520)",
+    "h2o4_631gs_rijk": "(H2O)_4 6-31G* RI-JK (smoke size)",
 }
 
 
@@ -185,7 +189,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    geo, shells, nocc = build_workload(args.workload)
+    # (the reference's RI path rebuilds the N^4 tensor and cannot run config 5 at all: its direct J/K is the comparator)
+    geo, shells, nocc = build_workload(args.workload[:-5] if args.workload.endswith("_rijk") else args.workload)
     orc, b = oracle_basis(shells)
     rng = np.random.default_rng(0)
     A = rng.standard_normal((b.N, b.N)) * 0.05
@@ -495,10 +500,143 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------- RI-JK workloads
+def run_ri(args):
+    """Config 5: RI-JK Fock build.  A step = J and K from the occupied orbitals through the C ABI (qlb_ri_build_jk_occ: host
+    C_occ in, host J and K out) -- the call is end to end by construction; `value` uses the device time of the contractions
+    (CUDA events inside the library, all-reduce included), `e2e` the wall time of the whole call.  The auxiliary index is
+    sharded over the ranks (one all-reduce of [J;K] per build)."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from quantumlab_jl_b200 import libqlb, workloads
+    from quantumlab_jl_b200.b200shells import B200Shells
+    from quantumlab_jl_b200.resolutionidentity import B200RI
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = libqlb.init(local)
+    if world > 1:
+        idbuf = C.create_string_buffer(128)
+        if rank == 0:
+            libqlb.check(lib.qlb_comm_unique_id(idbuf))
+        obj = [idbuf.raw]
+        dist.broadcast_object_list(obj, src=0)
+        libqlb.check(lib.qlb_comm_init(C.create_string_buffer(obj[0], 128), rank, world))
+    base = args.workload[:-len("_rijk")]
+    geo, shells, nocc = build_workload(base)
+    aux = workloads.jkfit_aux(geo)
+    dev = B200Shells(shells, tau=args.tau)
+    N = dev.nbf
+    t0 = time.time()
+    ri = B200RI(dev, aux)
+    t_setup = time.time() - t0
+    q0, nq = ri.slice()
+    S = dev.one_electron("overlap")
+    H = np.asfortranarray(dev.one_electron("kinetic") + dev.one_electron("nuclear", geo))
+    import scipy.linalg
+
+    _, v = scipy.linalg.eigh(H, S)
+    J, K = ri.build_jk_occ(np.asfortranarray(v[:, :nocc]))
+    _, v = scipy.linalg.eigh(H + 2 * J - K, S)
+    Cocc = np.asfortranarray(v[:, :nocc])  # occupied orbitals of SCF iteration 2
+    hC = torch.from_numpy(Cocc.reshape(-1, order="F").copy()).pin_memory()
+    hJ = torch.empty(N * N, dtype=torch.float64).pin_memory()
+    hK = torch.empty(N * N, dtype=torch.float64).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+    dp_ = C.POINTER(C.c_double)
+    ms = C.c_double()
+
+    def step():
+        libqlb.check(lib.qlb_ri_build_jk_occ(ri._h, C.cast(hC.data_ptr(), dp_), nocc, C.cast(hJ.data_ptr(), dp_), C.cast(hK.data_ptr(), dp_),
+                                             C.byref(ms)))
+        return ms.value
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step()
+    barrier()
+    wall0 = time.time()
+    dev_ms, wall_s = 0.0, 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        dev_ms += step()
+        wall_s += time.perf_counter() - t0
+    wall1 = time.time()
+    t = torch.tensor([dev_ms, wall_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t[0].item()) / args.steps
+    value = 1e3 / ms_per_step
+    e2e_value = args.steps / float(t[1].item())
+    clocks = sampler.stop(wall0, wall1)
+    Jn = hJ.numpy().reshape(N, N, order="F")
+    Kn = hK.numpy().reshape(N, N, order="F")
+    if rank == 0:
+        naux = ri.naux
+        flops = 3.0 * N * N * nocc * naux + 4.0 * (N * (N + 1) / 2) * naux  # RI-K (X, then lower K) + the two RI-J passes
+        peak = libqlb.fp64_tensor_peak_probe()
+        dfma = libqlb.fp64_peak_probe()
+        achieved = flops / (ms_per_step * 1e-3) * 1e-12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "name": args.workload, "nsh": len(shells), "nbf": N,
+                       "naux": naux, "nocc": nocc,
+                       "parallelism": f"auxiliary index sharded over {world} rank(s), 1 NCCL all-reduce of [J;K]",
+                       "l2": "flushed between steps (256 MB write)", "timing": "CUDA events inside qlb_ri_build_jk_occ, max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N * nocc * 8, "d2h_bytes_per_step": 2 * N * N * 8},
+            "gpu_launches": args.steps * (6 + 3 * ((nq + ri_qchunk(N, nq) - 1) // max(1, ri_qchunk(N, nq)))),
+            "roofline": {"bound": "tensor-fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                         "traffic": None, "kernel": "dmma::dgemm_kernel (X^Q = B^Q C_occ batched over Q; K += X X^T), hand-written mma.sync m8n8k4 f64",
+                         "peak_source": "DMMA microbenchmark measured in this run (qlb_fp64_tensor_peak_probe)", "dfma_tflops_measured": dfma,
+                         "algorithmic_flops_per_build": flops},
+            "ri_setup_s": t_setup, "b_bytes_this_rank": 8 * (N * (N + 1) // 2) * nq,
+            "symmetry_residual": float(max(np.abs(Jn - Jn.T).max(), np.abs(Kn - Kn.T).max())),
+        }
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+    ri.destroy()
+    if world > 1:
+        dist.barrier()
+        lib.qlb_comm_destroy()
+        dist.destroy_process_group()
+
+
+def ri_qchunk(N, nq):
+    return max(1, min(max(nq, 1), (1 << 30) // (N * N * 8)))
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload.endswith("_rijk"):
+        run_ri(args)
     else:
         run_ours(args)
 

@@ -141,7 +141,7 @@ int qlb_schedule_pieces(const double *cost, int nranks, int32_t *npieces, int32_
  * qlb_multi_build_jk / qlb_multi_fock: host buffers as qlb_build_jk / qlb_fock.  P (and H) go up to device 0 once and reach
  *                      the other devices over NVLink (grouped ncclBroadcast); every device evaluates its share of the quartet
  *                      rows of the build; ONE grouped all-reduce of [J;K]; device 0 symmetrises / assembles F and answers.
- * qlb_multi_basis0     the device-0 qlb_basis (for qlb_overlap, qlb_schwarz, qlb_scf_create, ...). */
+ * qlb_multi_basis0     the basis handle of device 0, e.g. for qlb_overlap, qlb_schwarz, qlb_scf_create. */
 typedef struct qlb_multi qlb_multi;
 int qlb_multi_create(int ngpu, int nsh, const double *centers, const int32_t *L, const int32_t *nprim, const double *exps,
                      const double *coefs, qlb_multi **out);
@@ -206,6 +206,7 @@ int qlb_dgemm_device(int transA, int transB, int M, int N, int K, double alpha, 
 int qlb_qlog(double x);        /* the integer screening rule's qlog(x) = ceil(8 log2 x), exact table form (tests) */
 int qlb_set_profiling(int on); /* time every class kernel with its own event pair (serialises the classes) */
 int qlb_fp64_peak_probe(double *tflops); /* DFMA microbenchmark: the measured FP64 roofline denominator */
+int qlb_fp64_tensor_peak_probe(double *tflops); /* DMMA (mma.sync m8n8k4 f64) microbenchmark: the RI contractions' denominator */
 /* Test hook: injects the schedule feedback a multi-rank run would have all-reduced (counts[2*qc] quartets,
  * counts[2*qc+1] primitive quartets, class_ms[qc] calibration time of class pair qc), so that ONE device can evaluate
  * every piece of the nranks-way deal with qlb_build_jk_device(rank = 0..nranks-1) and check that the pieces sum up. */

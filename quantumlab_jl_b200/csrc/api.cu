@@ -61,21 +61,24 @@ static void make_boys_table(std::vector<double> &tab) {
 }
 
 // ------------------------------------------------------------------ small kernels
-// K1: primitive-pair records, one warp per shell pair, lanes stride the na*nb primitive pairs (coalesced SoA writes)
+// K1: primitive-pair records, one warp per shell pair, lanes stride the pair's KEPT primitive pairs (coalesced SoA writes).
+// kept[kept_off[w] + t] = ia * nb + ib of the t-th kept primitive pair (host: prune_primitive_pairs)
 __global__ void pair_prim_kernel(int npairs, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
-                                 const int *__restrict__ pair_poff, const double *__restrict__ xyz,
-                                 const int *__restrict__ poff, const double *__restrict__ exps,
+                                 const int *__restrict__ pair_poff, const int *__restrict__ kept_off, const int *__restrict__ kept,
+                                 const double *__restrict__ xyz, const int *__restrict__ poff, const double *__restrict__ exps,
                                  const double *__restrict__ coefs, double2 *rec) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= npairs) return;
   const int a = pair_a[w], b = pair_b[w];
-  const int oa = poff[a], ob = poff[b], na = poff[a + 1] - oa, nb = poff[b + 1] - ob;
+  const int oa = poff[a], ob = poff[b], nb = poff[b + 1] - ob;
   const double Ax = xyz[3 * a], Ay = xyz[3 * a + 1], Az = xyz[3 * a + 2];
   const double Bx = xyz[3 * b], By = xyz[3 * b + 1], Bz = xyz[3 * b + 2];
   const double ab2 = (Ax - Bx) * (Ax - Bx) + (Ay - By) * (Ay - By) + (Az - Bz) * (Az - Bz);
   const size_t base = (size_t)pair_poff[w];  // tile layout: primitive t, field f at base + (3 t + f) * 32
-  for (int t = lane; t < na * nb; t += 32) {
-    const int ia = t / nb, ib = t - ia * nb;
+  const int k0 = kept_off[w], nk = kept_off[w + 1] - k0;
+  for (int t = lane; t < nk; t += 32) {
+    const int code = kept[k0 + t];
+    const int ia = code / nb, ib = code - ia * nb;
     const double al = exps[oa + ia], be = exps[ob + ib];
     const double p = al + be, ip = 1.0 / p;
     double2 *r = rec + base + (size_t)(3 * TILE_KET) * t;
@@ -99,6 +102,13 @@ __global__ void density_block_max_kernel(int nsh, int N, const int *__restrict__
   }
   q = __reduce_max_sync(0xffffffffu, q);
   if ((threadIdx.x & 31) == 0) atomicMax(dl + nsh * nsh, q);
+}
+
+// per build: the density bound of every pair's own shell block, in pair order (read coalesced by the screening walk)
+__global__ void pair_dl_kernel(int npairs, const int *__restrict__ pair_a, const int *__restrict__ pair_b, int nsh,
+                               const int *__restrict__ dl, int *pair_dl) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < npairs) pair_dl[g] = dl[pair_b[g] + nsh * pair_a[g]];
 }
 
 __global__ void symmetrize_kernel(int N, double *A) {
@@ -157,8 +167,14 @@ static int run_pair_prims(qlb_basis *b) {
   const int np = (int)b->npairs;
   if (np == 0) return QLB_OK;
   const int threads = 256, blocks = (int)(((int64_t)np * 32 + threads - 1) / threads);
-  pair_prim_kernel<<<blocks, threads, 0, e.stream>>>(np, b->d_pair_a, b->d_pair_b, b->d_pair_poff, b->d_xyz, b->d_poff,
-                                                     b->d_exps, b->d_coefs, b->d_pp);
+  // (re)upload the kept-primitive lists of the current pair order
+  if (b->d_kept_off) cudaFree(b->d_kept_off);
+  if (b->d_kept) cudaFree(b->d_kept);
+  b->d_kept_off = b->d_kept = nullptr;
+  if (int rc = upload(&b->d_kept_off, b->h_kept_off)) return rc;
+  if (int rc = upload(&b->d_kept, b->h_kept)) return rc;
+  pair_prim_kernel<<<blocks, threads, 0, e.stream>>>(np, b->d_pair_a, b->d_pair_b, b->d_pair_poff, b->d_kept_off, b->d_kept, b->d_xyz,
+                                                     b->d_poff, b->d_exps, b->d_coefs, b->d_pp);
   QLB_CUDA(cudaGetLastError());
   return QLB_OK;
 }
@@ -166,10 +182,44 @@ static int run_pair_prims(qlb_basis *b) {
 // Tile layout of the primitive-pair records: within each class (and RI group) the pairs are cut into tiles of 32
 // consecutive pairs (= the 32 ket lanes of a warp); a tile with Kmax primitive pairs in its longest pair owns
 // 3*32*Kmax double2 slots, ordered [primitive][field][lane].  h_pair_poff[i] = double2 index of (primitive 0, field 0).
+// Primitive-pair pruning (new functionality; the reference evaluates every primitive quartet): a primitive pair whose
+// prefactor |c_a c_b exp(-a b/(a+b) |AB|^2) / (a+b)| is below PRIM_PAIR_EPS cannot change any integral by more than
+// ~1e-19 (2 pi^2.5 |k_ab| |k_cd| / sqrt(p+q) x O(10) Hermite factors), eight orders below the 1e-10 parity bar; on
+// (H2O)32 / 6-31G* about half of the primitive pairs of the surviving shell pairs go.  The pairs that stay are listed
+// largest prefactor first; every shell pair keeps at least one.
+constexpr double PRIM_PAIR_EPS = 1e-22;
+static void prune_primitive_pairs(qlb_basis *b) {
+  b->h_kept_off.assign(b->npairs + 1, 0);
+  b->h_kept.clear();
+  std::vector<std::pair<double, int>> cand;
+  for (int64_t i = 0; i < b->npairs; ++i) {
+    const int a = b->h_pair_a[i], c = b->h_pair_b[i];
+    const int oa = b->h_poff[a], oc = b->h_poff[c], na = b->h_nprim[a], nc = b->h_nprim[c];
+    const double *A = &b->h_xyz[3 * a], *C = &b->h_xyz[3 * c];
+    const double ab2 = (A[0] - C[0]) * (A[0] - C[0]) + (A[1] - C[1]) * (A[1] - C[1]) + (A[2] - C[2]) * (A[2] - C[2]);
+    cand.clear();
+    for (int ia = 0; ia < na; ++ia)
+      for (int ic = 0; ic < nc; ++ic) {
+        const double al = b->h_exps[oa + ia], be = b->h_exps[oc + ic], p = al + be;
+        const double k = fabs(b->h_coefs[oa + ia] * b->h_coefs[oc + ic]) * exp(-al * be / p * ab2) / p;
+        cand.push_back({k, ia * nc + ic});
+      }
+    std::stable_sort(cand.begin(), cand.end(), [](const std::pair<double, int> &x, const std::pair<double, int> &y) { return x.first > y.first; });
+    int keep = 0;
+    for (const auto &cd : cand)
+      if (keep == 0 || cd.first >= PRIM_PAIR_EPS) {
+        b->h_kept.push_back(cd.second);
+        ++keep;
+      }
+    b->h_kept_off[i + 1] = (int)b->h_kept.size();
+  }
+}
+
 static void compute_pair_offsets(qlb_basis *b) {
   b->h_pair_poff.assign(b->npairs + 1, 0);
   b->h_pair_np.assign(std::max<int64_t>(b->npairs, 1), 0);
-  for (int64_t i = 0; i < b->npairs; ++i) b->h_pair_np[i] = b->h_nprim[b->h_pair_a[i]] * b->h_nprim[b->h_pair_b[i]];
+  prune_primitive_pairs(b);
+  for (int64_t i = 0; i < b->npairs; ++i) b->h_pair_np[i] = b->h_kept_off[i + 1] - b->h_kept_off[i];
   int64_t slot = 0;  // in double2 units
   auto layout = [&](int lo, int hi) {
     for (int t0 = lo; t0 < hi; t0 += TILE_KET) {
@@ -233,6 +283,7 @@ extern "C" int qlb_init(int device) {
   e.ysplit_full = getenv("QLB_YSPLIT_FULL") != nullptr;
   if (const char *v = getenv("QLB_BIN_W")) e.bin_width = std::max(1, atoi(v));
   e.no_schedule = getenv("QLB_NO_SCHEDULE") != nullptr;
+  e.no_dl_smem = getenv("QLB_NO_DLSMEM") != nullptr;
   e.ready = true;
   return QLB_OK;
 }
@@ -317,7 +368,7 @@ extern "C" int qlb_basis_destroy(qlb_basis *b) {
   if (b->eng) use_engine(b->eng);
   if (g_engine.ready) cudaSetDevice(g_engine.device);
   void *ptrs[] = {b->d_xyz, b->d_exps, b->d_coefs, b->d_poff, b->d_boff, b->d_L, b->d_pair_a, b->d_pair_b,
-                  b->d_pair_poff, b->d_pair_np, b->d_pair_ql, b->d_pair_qls, b->d_pair_Q, b->d_pp,
+                  b->d_pair_poff, b->d_pair_np, b->d_pair_ql, b->d_pair_qls, b->d_pair_Q, b->d_pp, b->d_pair_info, b->d_pair_dl, b->d_kept_off, b->d_kept,
                   b->d_P, b->d_JK, b->d_H, b->d_dl, b->d_counters, b->d_ms_local};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -462,6 +513,29 @@ static int basis_build_pairs(qlb_basis *b) {
   QLB_CUDA(cudaMemcpy(b->d_pair_np, b->h_pair_np.data(), b->npairs * sizeof(int), cudaMemcpyHostToDevice));
   QLB_CUDA(cudaMemcpy(b->d_pair_ql, b->h_pair_ql.data(), b->npairs * sizeof(int), cudaMemcpyHostToDevice));
   QLB_CUDA(cudaMemcpy(b->d_pair_qls, b->h_pair_qls.data(), b->npairs * sizeof(int), cudaMemcpyHostToDevice));
+  {
+    // packed per-pair records (eri_kernels.cuh: load_pair_info)
+    std::vector<double2> info((size_t)5 * std::max<int64_t>(b->npairs, 1));
+    for (int64_t i = 0; i < b->npairs; ++i) {
+      const int pa_ = b->h_pair_a[i], pb_ = b->h_pair_b[i];
+      const double *A = &b->h_xyz[3 * pa_], *B = &b->h_xyz[3 * pb_];
+      info[5 * i + 0] = make_double2(A[0], A[1]);
+      info[5 * i + 1] = make_double2(A[2], B[0]);
+      info[5 * i + 2] = make_double2(B[1], B[2]);
+      const int i3[4] = {pa_, pb_, b->h_pair_poff[i], b->h_pair_np[i]};
+      const int i4[4] = {b->h_boff[pa_], b->h_boff[pb_], b->h_pair_ql[i], 0};
+      memcpy(&info[5 * i + 3], i3, 16);
+      memcpy(&info[5 * i + 4], i4, 16);
+    }
+    if (b->d_pair_info) cudaFree(b->d_pair_info);
+    b->d_pair_info = nullptr;
+    QLB_CUDA(cudaMalloc((void **)&b->d_pair_info, info.size() * sizeof(double2)));
+    QLB_CUDA(cudaMemcpy(b->d_pair_info, info.data(), info.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    if (!b->d_pair_dl) {
+      QLB_CUDA(cudaMalloc((void **)&b->d_pair_dl, std::max<int64_t>(b->npairs, 1) * sizeof(int)));
+      QLB_CUDA(cudaMemset(b->d_pair_dl, 0, std::max<int64_t>(b->npairs, 1) * sizeof(int)));
+    }
+  }
   QLB_CUDA(cudaMemcpy(b->d_pair_Q, b->h_pair_Q.data(), b->npairs * sizeof(double), cudaMemcpyHostToDevice));
   if (int rc = run_pair_prims(b)) return rc;
   QLB_CUDA(cudaStreamSynchronize(e.stream));
@@ -583,6 +657,8 @@ static void base_params(qlb_basis *b, ClassParams &prm) {
   memset(&prm, 0, sizeof(prm));
   prm.sh_xyz = b->d_xyz; prm.sh_boff = b->d_boff; prm.nsh = b->nsh; prm.nbf = b->nbf;
   prm.pair_a = b->d_pair_a; prm.pair_b = b->d_pair_b; prm.pair_poff = b->d_pair_poff; prm.pair_np = b->d_pair_np; prm.pair_ql = b->d_pair_ql; prm.pair_qls = b->d_pair_qls;
+  prm.pair_dl = b->d_pair_dl; prm.pair_info = b->d_pair_info;
+  prm.dl_smem = (b->nsh <= DL_SMEM_MAX_NSH && !g_engine.no_dl_smem) ? 1 : 0;
   fill_pp(b, prm.pp);
   prm.boys = g_engine.d_boys;
   prm.dl = b->d_dl;
@@ -710,8 +786,9 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
     QLB_CUDA(cudaMemcpyAsync(b->d_dl + (size_t)nsh * nsh, &init, sizeof(int), cudaMemcpyHostToDevice, s));
     const int threads = 128, blocks = (nsh * nsh + threads - 1) / threads;
     density_block_max_kernel<<<blocks, threads, 0, s>>>(nsh, N, b->d_boff, dP, b->d_dl);
+    pair_dl_kernel<<<(unsigned)((b->npairs + 255) / 256), 256, 0, s>>>((int)b->npairs, b->d_pair_a, b->d_pair_b, nsh, b->d_dl, b->d_pair_dl);
     QLB_CUDA(cudaGetLastError());
-    ++launches;
+    launches += 2;
     QLB_CUDA(cudaMemcpyAsync(b->h_dlmax, b->d_dl + (size_t)nsh * nsh, sizeof(int), cudaMemcpyDeviceToHost, s));
     QLB_CUDA(cudaEventRecord(b->ev_dlmax, s));
     b->dlmax_pending = true;

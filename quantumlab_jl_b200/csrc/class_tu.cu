@@ -22,6 +22,9 @@
 #define QC_MINB 1
 #endif
 
+// dynamic shared memory of the register-flavour J/K kernels: TILE_BRA x 2 rows of the density-bound table (int16)
+#define QC_DLSMEM(prm) ((prm).dl_smem ? (size_t)TILE_BRA * 2 * (prm).nsh * sizeof(short) : (size_t)0)
+
 #define QC_CAT2(a, b, c, d) launch_qc_##a##b##c##d
 #define QC_CAT(a, b, c, d) QC_CAT2(a, b, c, d)
 #define QC_DCAT2(a, b, c, d, k) launch_qc_##a##b##c##d##_d##k
@@ -59,11 +62,11 @@ int QC_DCAT(QC_LA, QC_LB, QC_LC, QC_LD, QC_DSEL)(int mode, unsigned grid, cudaSt
 #else
   const dim3 block(TILE_KET, TILE_BRA);
 #if QC_UNR
-  if (mode == 0) unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, 1, QC_DSEL, QC_MINB><<<grid, block, 0, s>>>(prm);
+  if (mode == 0) unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, 1, QC_DSEL, QC_MINB><<<grid, block, QC_DLSMEM(prm), s>>>(prm);
   else unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, 1, QC_DSEL, QC_MINB><<<grid, block, 0, s>>>(prm);
 #else
   // rolled split classes also split over the ket-c components (gridDim.y): 6x more, 6x shorter threads
-  if (mode == 0) rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, 1, QC_DSEL, QC_MINB, true><<<dim3(grid, ncart(QC_LC)), block, 0, s>>>(prm);
+  if (mode == 0) rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, 1, QC_DSEL, QC_MINB, true><<<dim3(grid, ncart(QC_LC)), block, QC_DLSMEM(prm), s>>>(prm);
   else rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, 1, QC_DSEL, QC_MINB, false><<<grid, block, 0, s>>>(prm);
 #endif
   return (int)cudaGetLastError();
@@ -104,10 +107,10 @@ int QC_CAT(QC_LA, QC_LB, QC_LC, QC_LD)(int mode, unsigned grid, cudaStream_t s, 
 #elif QC_UNR == 2
     return launch_coop<0>(grid, s, prm);
 #elif QC_UNR
-    if (mode == 0) unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, QC_DSTEP, -1, QC_MINB><<<grid, block, 0, s>>>(prm);
+    if (mode == 0) unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, QC_DSTEP, -1, QC_MINB><<<grid, block, QC_DLSMEM(prm), s>>>(prm);
     else unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, QC_DSTEP, -1, QC_MINB><<<grid, block, 0, s>>>(prm);
 #else
-    if (mode == 0) rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, QC_DSTEP, -1, QC_MINB><<<grid, block, 0, s>>>(prm);
+    if (mode == 0) rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, QC_DSTEP, -1, QC_MINB><<<grid, block, QC_DLSMEM(prm), s>>>(prm);
     else rol::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, QC_DSTEP, -1, QC_MINB><<<grid, block, 0, s>>>(prm);
 #endif
   } else {

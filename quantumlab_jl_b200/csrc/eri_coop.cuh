@@ -93,7 +93,8 @@ struct CoopShape {
   static constexpr int P_DOUBLES = NA * NB;
   static constexpr int JC = (NA * NB < 18) ? NA * NB : 18;  // J_ab elements reduced across the warps per round
   static constexpr int J_DOUBLES = NW * JC * 32;
-  static constexpr size_t SMEM_BYTES = sizeof(double) * (R_DOUBLES + E_DOUBLES + B_DOUBLES + P_DOUBLES + J_DOUBLES);
+  // + 2 rows of the density-bound table as int16 (up to DL_SMEM_MAX_NSH shells), see the kernel
+  static constexpr size_t SMEM_BYTES = sizeof(double) * (R_DOUBLES + E_DOUBLES + B_DOUBLES + P_DOUBLES + J_DOUBLES) + 2 * DL_SMEM_MAX_NSH * sizeof(short);
 };
 
 // ---- R_tuv columns.  S1[n][v] = R^n_{0,0,v}; column (u,v): R^0_{t,u,v}, t = 0..L-u-v, built from the v-th
@@ -182,13 +183,13 @@ __host__ __device__ constexpr bool r_has_target(int r, int s, int w, int bx, int
   return false;
 }
 
-// ---- one thread's share of a primitive quartet: acc[a + NA*b] += (a b | c_IC d_ID)
+// ---- one thread's share of a primitive quartet, ket half: G[t u v] = sum E^{c_IC d_ID}_{t'u'v'} R_{t+t',u+u',v+v'}.  This is
+// the only code that differs between the warps of a CTA (one fully unrolled body per ket-c component)
 template <int LA, int LB, int LC, int LD, int IC, int ID>
-__device__ __forceinline__ void contract_cd(const double *__restrict__ Rl, const double *__restrict__ Es, double QCx,
-                                            double QDx, double QCy, double QDy, double QCz, double QDz, double oo2q,
-                                            double *acc) {
+__device__ __forceinline__ void ket_contract_cd(const double *__restrict__ Rl, double QCx, double QDx, double QCy, double QDy,
+                                                double QCz, double QDz, double oo2q, double (&G)[nherm(LA + LB)]) {
   using S = CoopShape<LA, LB, LC, LD>;
-  constexpr int L = S::L, LAB = S::LAB, NA = S::NA, NE1 = S::NE1;
+  constexpr int L = S::L, LAB = S::LAB;
   // ket Hermite coefficients (sign folded): only the rows of this thread's component pair survive dead-code elimination
   double Ecd[3][LC + 1][LD + 1][LC + LD + 1];
   unr::hermite_E<LC, LD, true>(Ecd[0], QCx, QDx, oo2q);
@@ -207,10 +208,9 @@ __device__ __forceinline__ void contract_cd(const double *__restrict__ Rl, const
       for (int vv = 0; vv <= bz; ++vv) ek[tt][uu][vv] = exy * Ecd[2][cz][dz][vv];
     }
   // ket contraction, scatter form: every needed R element is read from shared memory once
-  double G[nherm(LAB)];
 #pragma unroll
   for (int i = 0; i < nherm(LAB); ++i) G[i] = 0.0;
-  static_for<nherm(L)>([&](auto ric) {
+  static_for<nherm(L)>([&](auto ric) __attribute__((always_inline)) {
     constexpr int ridx = decltype(ric)::value;
     constexpr int r = herm_t(L, ridx), s = herm_u(L, ridx), w = herm_v(L, ridx);
     if constexpr (r_has_target(r, s, w, bx, by, bz, LAB)) {
@@ -227,9 +227,16 @@ __device__ __forceinline__ void contract_cd(const double *__restrict__ Rl, const
           }
     }
   });
-  // bra contraction: E^ab is CTA-uniform (shared memory, broadcast loads)
+}
+
+// ---- bra half, the SAME code for every warp: acc[a + NA*b] += sum_tuv E^{ab}_{tuv} G[t u v]; E^ab is CTA-uniform (shared
+// memory, broadcast loads).  Keeping it out of the per-component bodies halves the kernel's code (ncu: the cooperative
+// kernels stalled on instruction fetch, "no_instruction" 5-7 per issue, with six different bodies in flight per CTA)
+template <int LA, int LB>
+__device__ __forceinline__ void bra_contract(const double *__restrict__ Es, const double (&G)[nherm(LA + LB)], double *acc) {
+  constexpr int LAB = LA + LB, NA = ncart(LA), NE1 = (LA + 1) * (LB + 1) * (LAB + 1);
   const double *__restrict__ Ex = Es, *__restrict__ Ey = Es + NE1, *__restrict__ Ez = Es + 2 * NE1;
-  static_for<NA * S::NB>([&](auto abc) {
+  static_for<NA * ncart(LB)>([&](auto abc) __attribute__((always_inline)) {
     constexpr int iab = decltype(abc)::value, ia = iab % NA, ib = iab / NA;
     constexpr int ax = cart_x(LA, ia), ay = cart_y(LA, ia), az = LA - ax - ay;
     constexpr int bbx = cart_x(LB, ib), bby = cart_y(LB, ib), bbz = LB - bbx - bby;
@@ -250,16 +257,29 @@ __device__ __forceinline__ void contract_cd(const double *__restrict__ Rl, const
 
 // ---- J/K digestion of one thread's (c_IC, d_ID) slice: the ket-indexed updates leave as reductions, the J_ab
 // contribution I*P_cd is ADDED to tab[] (reduced over warps and lanes by the caller)
-template <int LA, int LB, int LC, int LD, int IC, int ID>
-__device__ __forceinline__ void digest_cd(const double *acc, bool active, double deg, int fa, int fb, int fc, int fd,
+// non-axial factor of Cartesian component `idx` (runtime) of a shell with angular momentum L (compile time)
+template <int L>
+__device__ __forceinline__ double nonaxial_idx(int idx) {
+  if (L < 2) return 1.0;
+  if (L == 2) return (idx == 1 || idx == 2 || idx == 4) ? 1.7320508075688772 : 1.0;  // xy, xz, yz
+  int i = 0, x = L, y = 0;
+  for (int xx = L; xx >= 0; --xx)
+    for (int yy = L - xx; yy >= 0; --yy, ++i)
+      if (i == idx) { x = xx; y = yy; }
+  return nonaxial(L, x, y, L - x - y);
+}
+
+// (the ket-c component ic is a RUNTIME value here: one copy of this code serves every warp)
+template <int LA, int LB, int LC, int LD, int ID>
+__device__ __forceinline__ void digest_cd(const double *acc, bool active, double deg, int fa, int fb, int fc, int fd, int ic,
                                           const double *__restrict__ Pab, const ClassParams &prm, double *tab) {
   constexpr int NA = ncart(LA), NB = ncart(LB);
-  constexpr int cx = cart_x(LC, IC), cy = cart_y(LC, IC), dx = cart_x(LD, ID), dy = cart_y(LD, ID);
+  constexpr int dx = cart_x(LD, ID), dy = cart_y(LD, ID);
   if (!active) return;  // (warp-divergent; no collective below)
   const int N = prm.nbf;
   const double *__restrict__ P = prm.P;
-  const int gc = fc + IC, gd = fd + ID;
-  const double ncd = nonaxial(LC, cx, cy, LC - cx - cy) * nonaxial(LD, dx, dy, LD - dx - dy) * deg;
+  const int gc = fc + ic, gd = fd + ID;
+  const double ncd = nonaxial_idx<LC>(ic) * nonaxial(LD, dx, dy, LD - dx - dy) * deg;
   const double pcd = __ldg(P + gc + (size_t)N * gd);
   double jcd = 0.0;
   double Kac[NA], Kad[NA], Kbc[NB], Kbd[NB];
@@ -273,13 +293,13 @@ __device__ __forceinline__ void digest_cd(const double *acc, bool active, double
     pad[ia] = __ldg(P + gd + (size_t)N * (fa + ia));
     pac[ia] = __ldg(P + gc + (size_t)N * (fa + ia));
   }
-  static_for<NB>([&](auto ibc) {
+  static_for<NB>([&](auto ibc) __attribute__((always_inline)) {
     constexpr int ib = decltype(ibc)::value;
     constexpr int bx = cart_x(LB, ib), by = cart_y(LB, ib);
     const double nb = nonaxial(LB, bx, by, LB - bx - by) * ncd;
     const double pbd = __ldg(P + gd + (size_t)N * (fb + ib));
     const double pbc = __ldg(P + gc + (size_t)N * (fb + ib));
-    static_for<NA>([&](auto iac) {
+    static_for<NA>([&](auto iac) __attribute__((always_inline)) {
       constexpr int ia = decltype(iac)::value;
       constexpr int ax = cart_x(LA, ia), ay = cart_y(LA, ia);
       const double v = acc[ia + NA * ib] * (nonaxial(LA, ax, ay, LA - ax - ay) * nb);
@@ -305,15 +325,15 @@ __device__ __forceinline__ void digest_cd(const double *acc, bool active, double
 }
 
 // ---- tensor mode: one thread's (c,d) slice into the N^4 tensor at its 8 symmetric positions
-template <int LA, int LB, int LC, int LD, int IC, int ID>
-__device__ __forceinline__ void scatter_cd(const double *acc, int fa, int fb, int fc, int fd, const ClassParams &prm) {
+template <int LA, int LB, int LC, int LD, int ID>
+__device__ __forceinline__ void scatter_cd(const double *acc, int fa, int fb, int fc, int fd, int ic, const ClassParams &prm) {
   constexpr int NA = ncart(LA), NB = ncart(LB);
-  constexpr int cx = cart_x(LC, IC), cy = cart_y(LC, IC), dx = cart_x(LD, ID), dy = cart_y(LD, ID);
+  constexpr int dx = cart_x(LD, ID), dy = cart_y(LD, ID);
   const size_t N = prm.nbf;
   double *T = prm.tensor;
-  const double ncd = nonaxial(LC, cx, cy, LC - cx - cy) * nonaxial(LD, dx, dy, LD - dx - dy);
-  const size_t c = fc + IC, d = fd + ID;
-  static_for<NA * NB>([&](auto abc) {
+  const double ncd = nonaxial_idx<LC>(ic) * nonaxial(LD, dx, dy, LD - dx - dy);
+  const size_t c = fc + ic, d = fd + ID;
+  static_for<NA * NB>([&](auto abc) __attribute__((always_inline)) {
     constexpr int iab = decltype(abc)::value, ia = iab % NA, ib = iab / NA;
     constexpr int ax = cart_x(LA, ia), ay = cart_y(LA, ia), bx = cart_x(LB, ib), by = cart_y(LB, ib);
     const double I = acc[iab] * (nonaxial(LA, ax, ay, LA - ax - ay) * nonaxial(LB, bx, by, LB - bx - by) * ncd);
@@ -329,13 +349,23 @@ __device__ __forceinline__ void scatter_cd(const double *acc, int fa, int fb, in
   });
 }
 
-// warp w runs the code of ket-c components w, w+NW, ..: f(integral_constant<IC>, integral_constant<slot>)
-template <int NC, int NW, int IC = 0>
+// warp w runs the code of ket-c components w, w+NW, ..: f(integral_constant<IC>, integral_constant<slot>).  Per slot the
+// NW candidates form ONE if / else-if chain (mutually exclusive branches: the register allocator must not think that
+// several of the fully unrolled component bodies can run back to back).
+template <int NW, int SLOT, int W = 0>
+struct CoopChain {
+  template <class F>
+  static __device__ __forceinline__ void run(int w, F &&f) {
+    if (w == W) f(std::integral_constant<int, SLOT * NW + W>(), std::integral_constant<int, SLOT>());
+    else if constexpr (W + 1 < NW) CoopChain<NW, SLOT, W + 1>::run(w, f);
+  }
+};
+template <int NC, int NW, int SLOT = 0>
 struct CoopDispatch {
   template <class F>
   static __device__ __forceinline__ void run(int w, F &&f) {
-    if ((IC % NW) == w) f(std::integral_constant<int, IC>(), std::integral_constant<int, IC / NW>());
-    if constexpr (IC + 1 < NC) CoopDispatch<NC, NW, IC + 1>::run(w, f);
+    CoopChain<NW, SLOT>::run(w, f);
+    if constexpr ((SLOT + 1) * NW < NC) CoopDispatch<NC, NW, SLOT + 1>::run(w, f);
   }
 };
 
@@ -345,7 +375,8 @@ template <int LA, int LB, int LC, int LD, int DSEL, int CPT, int MINB>
 __global__ void __launch_bounds__(32 * (ncart(LC) / CPT), MINB) eri_coop_kernel(const __grid_constant__ ClassParams prm) {
   using S = CoopShape<LA, LB, LC, LD, CPT>;
   constexpr int NW = S::NW, NC = ncart(LC), L = S::L, NA = S::NA, NB = S::NB, NAB = NA * NB, NE1 = S::NE1, JC = S::JC;
-  __shared__ int s_queue[NW][64];  // per-warp (identical) queues of surviving ket pairs
+  constexpr int QUEUE_NBK = 4;
+  __shared__ int s_queue[NW][QUEUE_NBK * 64];  // per-warp (identical) queues of surviving ket pairs, bucketed by contraction
   extern __shared__ double coop_smem[];
   double *Rs = coop_smem;
   double *Es = Rs + S::R_DOUBLES;
@@ -374,138 +405,36 @@ __global__ void __launch_bounds__(32 * (ncart(LC) / CPT), MINB) eri_coop_kernel(
     if (prm.screen && prm.pair_qls[prm.bra_off + ib] + prm.pair_qls[prm.ket_off + ik0] + dlmax < prm.tlog) break;
   }
   const int gb = prm.bra_off + ib;
-  const int sa = prm.pair_a[gb], sb = prm.pair_b[gb];
-  const int qlb = prm.pair_ql[gb];
-  const int bra_off = prm.pair_poff[gb], bra_np = prm.pair_np[gb];
-  const double Ax = prm.sh_xyz[3 * sa], Ay = prm.sh_xyz[3 * sa + 1], Az = prm.sh_xyz[3 * sa + 2];
-  const double Bx = prm.sh_xyz[3 * sb], By = prm.sh_xyz[3 * sb + 1], Bz = prm.sh_xyz[3 * sb + 2];
-  const int fa = prm.sh_boff[sa], fb = prm.sh_boff[sb];
+  const PairInfo bi = load_pair_info(prm.pair_info, gb);
+  const int sa = bi.a, sb = bi.b;
+  const int qlb = bi.ql;
+  const int bra_off = bi.poff, bra_np = bi.np;
+  const double Ax = bi.Ax, Ay = bi.Ay, Az = bi.Az;
+  const double Bx = bi.Bx, By = bi.By, Bz = bi.Bz;
+  const int fa = bi.fa, fb = bi.fb;
   const double degab = (sa == sb) ? 1.0 : 2.0;
   const int dab = prm.screen ? dl[sa + nsh * sb] : 0;
   __syncthreads();  // the previous bra pair's readers of Pab / E^ab are done
   if (!tensor_mode)
     for (int i = tid; i < NAB; i += 32 * NW) Pab[i] = prm.P[(fa + i % NA) + (size_t)prm.nbf * (fb + i / NA)];
+  // rows dl[., sa], dl[., sb] of the density-bound table for the screening walk (see eri_body.inc)
+  const bool dl_sm = prm.screen && prm.dl_smem;
+  short *dla = reinterpret_cast<short *>(Js + S::J_DOUBLES), *dlb = dla + nsh;
+  if (dl_sm) {
+    for (int i = tid; i < nsh; i += 32 * NW) {
+      dla[i] = (short)max(dl[i + nsh * sa], -32768);
+      dlb[i] = (short)max(dl[i + nsh * sb], -32768);
+    }
+    __syncthreads();
+  }
   int chunk_loaded = -1;
 
   // ---- one batch of (up to 32) quartets of the CTA's bra pair: lane -> ket pair ik of the class (identical in every warp)
-  auto process = [&](const int ik, const bool active) {
-    const int gk = prm.ket_off + min(max(ik, 0), prm.ket_n - 1);
-    const int sc = prm.pair_a[gk], sd = prm.pair_b[gk];
-    const int ket_off = prm.pair_poff[gk];
-    const int ket_np = prm.pair_np[gk];
-    const int kmax = __reduce_max_sync(0xffffffffu, active ? ket_np : 0);
-    if (active && w == 0) { n_q += 1u; n_pq += (unsigned)(bra_np * ket_np); }
-    const double Cx = prm.sh_xyz[3 * sc], Cy = prm.sh_xyz[3 * sc + 1], Cz = prm.sh_xyz[3 * sc + 2];
-    const double Dx = prm.sh_xyz[3 * sd], Dy = prm.sh_xyz[3 * sd + 1], Dz = prm.sh_xyz[3 * sd + 2];
-    double acc[CPT][NAB];
-#pragma unroll
-    for (int k = 0; k < CPT; ++k)
-#pragma unroll
-      for (int i = 0; i < NAB; ++i) acc[k][i] = 0.0;
-
-#pragma unroll 1
-    for (int ip0 = 0; ip0 < bra_np; ip0 += COOP_MAXBP) {
-      const int nchunk = min(COOP_MAXBP, bra_np - ip0);
-      if (chunk_loaded != ip0) {  // CTA-uniform
-        __syncthreads();
-        if (tid < 3 * nchunk) {
-          const int pi = tid / 3, axis = tid - 3 * pi;
-          const double2 *rb = prm.pp.rec + (size_t)bra_off + (size_t)(3 * TILE_KET) * (ip0 + pi);
-          const double2 b0 = __ldg(rb), b1 = __ldg(rb + TILE_KET), b2 = __ldg(rb + 2 * TILE_KET);
-          const double Pc = axis == 0 ? b0.y : (axis == 1 ? b1.x : b1.y);
-          const double Ac = axis == 0 ? Ax : (axis == 1 ? Ay : Az);
-          const double Bc = axis == 0 ? Bx : (axis == 1 ? By : Bz);
-          double E[LA + 1][LB + 1][LA + LB + 1];
-          unr::hermite_E<LA, LB, false>(E, Pc - Ac, Pc - Bc, b2.y);
-          double *dst = Es + (size_t)(pi * 3 + axis) * NE1;
-#pragma unroll
-          for (int i = 0; i <= LA; ++i)
-#pragma unroll
-            for (int j = 0; j <= LB; ++j)
-#pragma unroll
-              for (int t = 0; t <= LA + LB; ++t) dst[(i * (LB + 1) + j) * (LA + LB + 1) + t] = (t <= i + j) ? E[i][j][t] : 0.0;
-          if (axis == 0) {
-            double *br = Bs + pi * 8;
-            br[0] = b0.x; br[1] = b0.y; br[2] = b1.x; br[3] = b1.y; br[4] = b2.x;
-          }
-        }
-        chunk_loaded = ip0;
-        __syncthreads();
-      }
-#pragma unroll 1
-      for (int pi = 0; pi < nchunk; ++pi) {
-        const double p = Bs[pi * 8], Px = Bs[pi * 8 + 1], Py = Bs[pi * 8 + 2], Pz = Bs[pi * 8 + 3], kab = Bs[pi * 8 + 4];
-        const double *Ep = Es + (size_t)(pi * 3) * NE1;
-#pragma unroll 1
-        for (int iq = 0; iq < kmax; ++iq) {
-          const bool on = active && iq < ket_np;
-          const double2 *rk = prm.pp.rec + (size_t)ket_off + (size_t)(3 * TILE_KET) * min(iq, ket_np - 1);
-          const double2 k0 = __ldg(rk), k1 = __ldg(rk + TILE_KET), k2 = __ldg(rk + 2 * TILE_KET);
-          const double q = k0.x, Qx = k0.y, Qy = k1.x, Qz = k1.y;
-          const double r = rsqrt(p + q);
-          const double alpha = p * q * (r * r);
-          const double X = Px - Qx, Y = Py - Qy, Z = Pz - Qz;
-          const double T = alpha * (X * X + Y * Y + Z * Z);
-          const double pref = on ? QLB_TWO_PI_52 * kab * k2.x * r : 0.0;
-          double F[L + 1];
-          boys_array<L>(T, s_boys, F);
-          {
-            double sgn = pref;  // pref * (-2 alpha)^n
-#pragma unroll
-            for (int n = 0; n <= L; ++n) {
-              F[n] *= sgn;
-              sgn *= -2.0 * alpha;
-            }
-          }
-          build_R_columns<L, NW>(F, X, Y, Z, w, Rl);
-          __syncthreads();
-          CoopDispatch<NC, NW>::run(w, [&](auto icc, auto slot) {
-            contract_cd<LA, LB, LC, LD, decltype(icc)::value, DSEL>(Rl, Ep, Qx - Cx, Qx - Dx, Qy - Cy, Qy - Dy, Qz - Cz, Qz - Dz,
-                                                                    k2.y, acc[decltype(slot)::value]);
-          });
-          __syncthreads();
-        }
-      }
-    }
-    // ---- digestion / scatter of this thread's slices
-    const int fc = prm.sh_boff[sc], fd = prm.sh_boff[sd];
-    if (!tensor_mode) {
-      const double deg = degab * ((sc == sd) ? 1.0 : 2.0) * ((prm.same && ib == ik) ? 1.0 : 2.0);
-      double tab[NAB];  // this thread's J_ab contribution (all its ket-c components)
-#pragma unroll
-      for (int i = 0; i < NAB; ++i) tab[i] = 0.0;
-      CoopDispatch<NC, NW>::run(w, [&](auto icc, auto slot) {
-        digest_cd<LA, LB, LC, LD, decltype(icc)::value, DSEL>(acc[decltype(slot)::value], active, deg, fa, fb, fc, fd, Pab, prm, tab);
-      });
-      // J_ab: sum over the warps through shared memory, then over the lanes; JC elements per round
-      static_for<(NAB + JC - 1) / JC>([&](auto rc) {
-        constexpr int c0 = decltype(rc)::value * JC;
-        static_for<JC>([&](auto ic) {
-          constexpr int i = decltype(ic)::value;
-          Js[(w * JC + i) * 32 + lane] = (c0 + i < NAB) ? tab[c0 + i < NAB ? c0 + i : 0] : 0.0;
-        });
-        __syncthreads();
-        for (int i = w; i < JC && c0 + i < NAB; i += NW) {
-          double s = 0.0;
-#pragma unroll
-          for (int ww = 0; ww < NW; ++ww) s += Js[(ww * JC + i) * 32 + lane];
-          s = warp_sum(s);
-          const int iab = c0 + i;
-          if (lane == 0 && s != 0.0) atomicAdd(prm.J + (fa + iab % NA) + (size_t)prm.nbf * (fb + iab / NA), 0.5 * s);
-        }
-        __syncthreads();
-      });
-    } else if (active) {
-      CoopDispatch<NC, NW>::run(w, [&](auto icc, auto slot) {
-        scatter_cd<LA, LB, LC, LD, decltype(icc)::value, DSEL>(acc[decltype(slot)::value], fa, fb, fc, fd, prm);
-      });
-    }
-  };
   // Survivor compaction as in the register flavour (eri_body.inc): every warp of the CTA runs the same screening walk and
   // keeps its own, identical copy of the queue, so all warps call process() the same number of times (it synchronises).
-  int qn = 0;
+  unsigned qn = 0;  // queued survivors per contraction bucket, 8 bits each (identical in every warp)
   int *queue = s_queue[w];
-  // one loop, one call site of process() (so that it is inlined): the last trip only drains the queue
+  // one loop, one textual copy of the batch body: the last trip only drains the queues
 #pragma unroll 1
   for (int bxk = y;; bxk += prm.ysplit) {
     const int ik0 = bxk * TILE_KET;
@@ -513,6 +442,7 @@ __global__ void __launch_bounds__(32 * (ncart(LC) / CPT), MINB) eri_coop_kernel(
     if (!last && prm.screen && prm.pair_qls[gb] + prm.pair_qls[prm.ket_off + ik0] + dlmax < prm.tlog) last = true;
     const int ik = ik0 + lane;
     bool active = false;
+    int bucket = 0;
     if (!last) {
       active = ik < prm.ket_n && (!prm.same || ik <= ib);
       if (prm.screen && active) {
@@ -521,33 +451,180 @@ __global__ void __launch_bounds__(32 * (ncart(LC) / CPT), MINB) eri_coop_kernel(
         if (s + dlmax < prm.tlog) active = false;
         else {
           const int sc = prm.pair_a[gk], sd = prm.pair_b[gk];
-          int dm = max(dab, dl[sd + nsh * sc]);
-          dm = max(dm, max(dl[sc + nsh * sa], dl[sd + nsh * sa]));
-          dm = max(dm, max(dl[sc + nsh * sb], dl[sd + nsh * sb]));
+          int dm = max(dab, prm.pair_dl[gk]);
+          if (dl_sm) {
+            dm = max(dm, max((int)dla[sc], (int)dla[sd]));
+            dm = max(dm, max((int)dlb[sc], (int)dlb[sd]));
+          } else {
+            dm = max(dm, max(dl[sc + nsh * sa], dl[sd + nsh * sa]));
+            dm = max(dm, max(dl[sc + nsh * sb], dl[sd + nsh * sb]));
+          }
           active = (s + dm >= prm.tlog);
         }
       }
+      if (!tensor_mode && active) {
+        const int np = prm.pair_np[prm.ket_off + ik];
+        bucket = (np > 1) + (np > 4) + (np > 12);
+      }
     }
     const unsigned m = __ballot_sync(0xffffffffu, active);  // identical in every warp of the CTA
-    int ikc = ik;
-    bool act = active, run = m != 0u;
     if (!tensor_mode) {
-      if (active) queue[qn + __popc(m & ((1u << lane) - 1u))] = ik;
-      qn += __popc(m);
+#pragma unroll
+      for (int k = 0; k < QUEUE_NBK; ++k) {
+        const unsigned mk = __ballot_sync(0xffffffffu, active && bucket == k);
+        const int cnt = (qn >> (8 * k)) & 0xffu;
+        if (active && bucket == k) queue[64 * k + cnt + __popc(mk & ((1u << lane) - 1u))] = ik;
+        qn += (unsigned)__popc(mk) << (8 * k);
+      }
       __syncwarp();
-      run = qn >= 32 || (last && qn > 0);
+    }
+#pragma unroll 1
+    for (bool first = true;; first = false) {  // drain: every bucket that holds a full batch (at the end: anything)
+    int ikc = ik;
+    bool act = active, run = first && m != 0u;
+    if (!tensor_mode) {
+      int kb = -1;
+#pragma unroll
+      for (int k = QUEUE_NBK - 1; k >= 0; --k) {
+        const int cnt = (qn >> (8 * k)) & 0xffu;
+        if (cnt >= 32 || (last && cnt > 0)) kb = k;
+      }
+      run = kb >= 0;
       if (run) {
-        const int take = min(qn, 32), rest = qn - take;
+        const int cnt = (qn >> (8 * kb)) & 0xffu;
+        const int take = min(cnt, 32), rest = cnt - take;
+        int *qb = queue + 64 * kb;
         act = lane < take;
-        ikc = act ? queue[lane] : 0;
-        const int carry = (lane < rest) ? queue[32 + lane] : 0;
+        ikc = act ? qb[lane] : 0;
+        const int carry = (lane < rest) ? qb[32 + lane] : 0;
         __syncwarp();
-        if (lane < rest) queue[lane] = carry;
-        qn = rest;
+        if (lane < rest) qb[lane] = carry;
+        qn -= (unsigned)take << (8 * kb);
         __syncwarp();
       }
     }
-    if (run) process(ikc, act);
+    if (!run) break;
+    {  // one batch: lane -> ket pair ikc of the class (textually inlined: nvcc does not inline a lambda this large)
+      const int ik = ikc;
+      const bool active = act;
+      const int gk = prm.ket_off + min(max(ik, 0), prm.ket_n - 1);
+      const PairInfo ki = load_pair_info(prm.pair_info, gk);
+      const int sc = ki.a, sd = ki.b;
+      const int ket_off = ki.poff;
+      const int ket_np = ki.np;
+      const int kmax = __reduce_max_sync(0xffffffffu, active ? ket_np : 0);
+      if (active && w == 0) { n_q += 1u; n_pq += (unsigned)(bra_np * ket_np); }
+      const double Cx = ki.Ax, Cy = ki.Ay, Cz = ki.Az;
+      const double Dx = ki.Bx, Dy = ki.By, Dz = ki.Bz;
+      double acc[CPT][NAB];
+  #pragma unroll
+      for (int k = 0; k < CPT; ++k)
+  #pragma unroll
+        for (int i = 0; i < NAB; ++i) acc[k][i] = 0.0;
+
+  #pragma unroll 1
+      for (int ip0 = 0; ip0 < bra_np; ip0 += COOP_MAXBP) {
+        const int nchunk = min(COOP_MAXBP, bra_np - ip0);
+        if (chunk_loaded != ip0) {  // CTA-uniform
+          __syncthreads();
+          if (tid < 3 * nchunk) {
+            const int pi = tid / 3, axis = tid - 3 * pi;
+            const double2 *rb = prm.pp.rec + (size_t)bra_off + (size_t)(3 * TILE_KET) * (ip0 + pi);
+            const double2 b0 = __ldg(rb), b1 = __ldg(rb + TILE_KET), b2 = __ldg(rb + 2 * TILE_KET);
+            const double Pc = axis == 0 ? b0.y : (axis == 1 ? b1.x : b1.y);
+            const double Ac = axis == 0 ? Ax : (axis == 1 ? Ay : Az);
+            const double Bc = axis == 0 ? Bx : (axis == 1 ? By : Bz);
+            double E[LA + 1][LB + 1][LA + LB + 1];
+            unr::hermite_E<LA, LB, false>(E, Pc - Ac, Pc - Bc, b2.y);
+            double *dst = Es + (size_t)(pi * 3 + axis) * NE1;
+  #pragma unroll
+            for (int i = 0; i <= LA; ++i)
+  #pragma unroll
+              for (int j = 0; j <= LB; ++j)
+  #pragma unroll
+                for (int t = 0; t <= LA + LB; ++t) dst[(i * (LB + 1) + j) * (LA + LB + 1) + t] = (t <= i + j) ? E[i][j][t] : 0.0;
+            if (axis == 0) {
+              double *br = Bs + pi * 8;
+              br[0] = b0.x; br[1] = b0.y; br[2] = b1.x; br[3] = b1.y; br[4] = b2.x;
+            }
+          }
+          chunk_loaded = ip0;
+          __syncthreads();
+        }
+  #pragma unroll 1
+        for (int pi = 0; pi < nchunk; ++pi) {
+          const double p = Bs[pi * 8], Px = Bs[pi * 8 + 1], Py = Bs[pi * 8 + 2], Pz = Bs[pi * 8 + 3], kab = Bs[pi * 8 + 4];
+          const double *Ep = Es + (size_t)(pi * 3) * NE1;
+  #pragma unroll 1
+          for (int iq = 0; iq < kmax; ++iq) {
+            const bool on = active && iq < ket_np;
+            const double2 *rk = prm.pp.rec + (size_t)ket_off + (size_t)(3 * TILE_KET) * min(iq, ket_np - 1);
+            const double2 k0 = __ldg(rk), k1 = __ldg(rk + TILE_KET), k2 = __ldg(rk + 2 * TILE_KET);
+            const double q = k0.x, Qx = k0.y, Qy = k1.x, Qz = k1.y;
+            const double r = rsqrt(p + q);
+            const double alpha = p * q * (r * r);
+            const double X = Px - Qx, Y = Py - Qy, Z = Pz - Qz;
+            const double T = alpha * (X * X + Y * Y + Z * Z);
+            const double pref = on ? QLB_TWO_PI_52 * kab * k2.x * r : 0.0;
+            double F[L + 1];
+            boys_array<L>(T, s_boys, F);
+            {
+              double sgn = pref;  // pref * (-2 alpha)^n
+  #pragma unroll
+              for (int n = 0; n <= L; ++n) {
+                F[n] *= sgn;
+                sgn *= -2.0 * alpha;
+              }
+            }
+            build_R_columns<L, NW>(F, X, Y, Z, w, Rl);
+            __syncthreads();
+            static_for<CPT>([&](auto slotc) __attribute__((always_inline)) {
+              constexpr int slot = decltype(slotc)::value;
+              double G[nherm(LA + LB)];
+              CoopChain<NW, slot>::run(w, [&](auto icc, auto) __attribute__((always_inline)) {
+                ket_contract_cd<LA, LB, LC, LD, decltype(icc)::value, DSEL>(Rl, Qx - Cx, Qx - Dx, Qy - Cy, Qy - Dy, Qz - Cz, Qz - Dz, k2.y, G);
+              });
+              bra_contract<LA, LB>(Ep, G, acc[slot]);
+            });
+            __syncthreads();
+          }
+        }
+      }
+      // ---- digestion / scatter of this thread's slices
+      const int fc = ki.fa, fd = ki.fb;
+      if (!tensor_mode) {
+        const double deg = degab * ((sc == sd) ? 1.0 : 2.0) * ((prm.same && ib == ik) ? 1.0 : 2.0);
+        double tab[NAB];  // this thread's J_ab contribution (all its ket-c components)
+  #pragma unroll
+        for (int i = 0; i < NAB; ++i) tab[i] = 0.0;
+#pragma unroll
+        for (int slot = 0; slot < CPT; ++slot)
+          digest_cd<LA, LB, LC, LD, DSEL>(acc[slot], active, deg, fa, fb, fc, fd, slot * NW + w, Pab, prm, tab);
+        // J_ab: sum over the warps through shared memory, then over the lanes; JC elements per round
+        static_for<(NAB + JC - 1) / JC>([&](auto rc) __attribute__((always_inline)) {
+          constexpr int c0 = decltype(rc)::value * JC;
+          static_for<JC>([&](auto ic) __attribute__((always_inline)) {
+            constexpr int i = decltype(ic)::value;
+            Js[(w * JC + i) * 32 + lane] = (c0 + i < NAB) ? tab[c0 + i < NAB ? c0 + i : 0] : 0.0;
+          });
+          __syncthreads();
+          for (int i = w; i < JC && c0 + i < NAB; i += NW) {
+            double s = 0.0;
+  #pragma unroll
+            for (int ww = 0; ww < NW; ++ww) s += Js[(ww * JC + i) * 32 + lane];
+            s = warp_sum(s);
+            const int iab = c0 + i;
+            if (lane == 0 && s != 0.0) atomicAdd(prm.J + (fa + iab % NA) + (size_t)prm.nbf * (fb + iab / NA), 0.5 * s);
+          }
+          __syncthreads();
+        });
+      } else if (active) {
+#pragma unroll
+        for (int slot = 0; slot < CPT; ++slot) scatter_cd<LA, LB, LC, LD, DSEL>(acc[slot], fa, fb, fc, fd, slot * NW + w, prm);
+      }
+    }
+    if (tensor_mode) break;  // no queues: one direct batch per tile
+    }  // drain
     if (last) break;
   }
   }  // bra pairs

@@ -16,6 +16,7 @@ namespace qlb {
 
 constexpr int TILE_KET = 32;  // = warp size: lanes of a warp share the bra pair
 constexpr int TILE_BRA = 4;   // warps per CTA
+constexpr int DL_SMEM_MAX_NSH = 2048;  // above this the screening reads dl from global memory
 
 // exact integer "quantised log": qlog(x) = ceil(8*log2(x)) evaluated without transcendental functions, so the
 // host, the device and the CPU oracle agree bit for bit.  x = m*2^e, m in [1,2):  8e + #{j in 0..7 : m > 2^(j/8)}.
@@ -60,6 +61,12 @@ struct ClassParams {
   const int *__restrict__ pair_np;     // per pair: number of primitive pairs
   const int *__restrict__ pair_ql;     // qlog(Q_ab)
   const int *__restrict__ pair_qls;    // max of pair_ql over this and every LATER pair of the class (non-increasing: ends walks)
+  const int *__restrict__ pair_dl;     // per build: qlog(max |P|) over the pair's own shell block (coalesced in the walk)
+  // packed per-pair record, 5 x 16 B: {Ax,Ay} {Az,Bx} {By,Bz} int4{a,b,poff,np} int4{fa,fb,ql,0}: what a batch needs about a
+  // ket pair arrives with 5 vector loads instead of 14 scattered scalar ones (ncu: the light classes are bound by L1
+  // wavefronts of exactly those gathers)
+  const double2 *__restrict__ pair_info;
+  int dl_smem;                         // 1: the kernels stage the bra shells' rows of dl in shared memory (nsh <= QLB_DL_SMEM_MAX_NSH)
   PrimPairs pp;
   const double *__restrict__ boys;
   // this launch: class ranges
@@ -82,6 +89,20 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+struct PairInfo {  // unpacked pair_info record
+  double Ax, Ay, Az, Bx, By, Bz;
+  int a, b, poff, np, fa, fb, ql;
+};
+__device__ __forceinline__ PairInfo load_pair_info(const double2 *__restrict__ info, int g) {
+  const double2 *r = info + (size_t)5 * g;
+  const double2 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+  const int4 i3 = __ldg(reinterpret_cast<const int4 *>(r + 3)), i4 = __ldg(reinterpret_cast<const int4 *>(r + 4));
+  PairInfo o;
+  o.Ax = r0.x; o.Ay = r0.y; o.Az = r1.x; o.Bx = r1.y; o.By = r2.x; o.Bz = r2.y;
+  o.a = i3.x; o.b = i3.y; o.poff = i3.z; o.np = i3.w; o.fa = i4.x; o.fb = i4.y; o.ql = i4.z;
+  return o;
 }
 
 struct QuartetCtx {

@@ -30,7 +30,7 @@ __host__ __device__ constexpr int hidx(int L, int t, int u, int v) {
 // their table in shared memory (ncu: with the table in global memory the low classes were bound by L1 wavefronts,
 // every lane touching its own row).  F_L(T) by an 8-term Taylor expansion about the nearest row, lower orders by
 // downward recursion with exp(-T) = exp(-T_i) * poly(T_i - T); beyond the table the asymptotic F_0 and upward
-// recursion.  Accurate to ~1e-15 relative.
+// recursion (without the exp(-T) term, which is below rounding there).  Accurate to ~2e-15 relative.
 constexpr int BOYS_ROWLEN = 10;
 constexpr int BOYS_LMAX = 8;            // (dd|dd)
 constexpr double BOYS_DT = 0.1;
@@ -61,15 +61,25 @@ __device__ __forceinline__ void boys_array(double T, const double *tab, double *
 #pragma unroll
       for (int m = L; m >= 1; --m) F[m - 1] = fma(t2, F[m], e) * (1.0 / (2 * m - 1));
     }
+  } else if constexpr (L <= 2) {
+    // T >= 36, low orders: F_0 = sqrt(pi/T)/2 and the upward recursion WITHOUT its exp(-T) term: exp(-36) = 2.3e-16 is
+    // below the rounding error of the terms it is added to (relative 1.6e-15 for F_1, 4e-14 for F_2 at T = 36, smaller
+    // beyond; for higher orders the term matters -- F_8(36) ~ 4e-10 -- so they keep it).  ncu: most primitive quartets of
+    // a screened build take this branch, and with exp() it cost more instructions than the table branch.
+    const double rs = rsqrt(T);
+    F[0] = 0.88622692545275801365 * rs;  // sqrt(pi)/2 / sqrt(T)
+    if (L > 0) {
+      const double i2t = 0.5 * (rs * rs);
+#pragma unroll
+      for (int m = 0; m < L; ++m) F[m + 1] = (double)(2 * m + 1) * F[m] * i2t;
+    }
   } else {
     const double it = 1.0 / T;
     F[0] = 0.5 * sqrt(QLB_PI * it);
-    if (L > 0) {
-      const double e = exp(-T);
-      const double i2t = 0.5 * it;
+    const double e = exp(-T);
+    const double i2t = 0.5 * it;
 #pragma unroll
-      for (int m = 0; m < L; ++m) F[m + 1] = fma((double)(2 * m + 1), F[m], -e) * i2t;
-    }
+    for (int m = 0; m < L; ++m) F[m + 1] = fma((double)(2 * m + 1), F[m], -e) * i2t;
   }
 }
 

@@ -39,7 +39,7 @@ struct Engine {
   // width (in qlog units, 8 per factor 2) of the Schwarz-bound bins of the pair order; 1 = exact order of the bounds.
   // Measured on (H2O)32: wider bins (index-local tiles) LOSE -- 45.5 / 54 / 62 / 74 / 85 ms per build for 1 / 8 / 16 / 32 / 64
   int bin_width = 1;
-  bool ysplit_full = false, no_schedule = false;
+  bool ysplit_full = false, no_schedule = false, no_dl_smem = false;
   // NCCL (loaded lazily with dlopen)
   void *nccl_lib = nullptr;
   void *nccl_comm = nullptr;
@@ -66,6 +66,8 @@ struct qlb_basis {
   int64_t npairs = 0;
   std::vector<int> h_pair_a, h_pair_b, h_pair_poff, h_pair_np, h_pair_ql, h_pair_qls;
   std::vector<double> h_pair_Q;
+  std::vector<int> h_kept_off, h_kept;  // kept primitive pairs per shell pair (CSR; code = ia * nprim_b + ib), see api.cu
+  int *d_kept_off = nullptr, *d_kept = nullptr;
   int class_off[qlb::NCLASS + 1] = {0};
   // resolution of the identity: shells [0,n_orb) orbital, [n_orb, nsh-1) auxiliary, shell nsh-1 the unit s function;
   // pair group 0 = orbital pairs (class_off), group 1 = (aux, unit) pairs (ri_class_off).  n_orb == 0: ordinary basis
@@ -81,6 +83,8 @@ struct qlb_basis {
   int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pair_poff = nullptr, *d_pair_np = nullptr, *d_pair_ql = nullptr, *d_pair_qls = nullptr;
   double *d_pair_Q = nullptr;
   double2 *d_pp = nullptr;  // 3 double2 per primitive pair: {p,Px} {Py,Pz} {k/p, 1/(2p)}
+  double2 *d_pair_info = nullptr;  // 5 double2 per pair: packed centres / indices (eri_kernels.cuh: load_pair_info)
+  int *d_pair_dl = nullptr;        // per build: density bound of the pair's own shell block
   int64_t nprimpairs = 0;
   // per-build scratch
   double *d_P = nullptr, *d_JK = nullptr, *d_H = nullptr;  // N*N, 2*N*N, N*N

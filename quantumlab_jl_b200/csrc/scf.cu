@@ -278,3 +278,52 @@ extern "C" int qlb_dgemm_device(int ta, int tb, int M, int N, int K, double alph
   if (ce != cudaSuccess) return cuda_fail(ce, "dgemm");
   return QLB_OK;
 }
+
+// DMMA microbenchmark: the measured FP64 tensor-core roofline denominator of the RI contractions.  8 independent
+// accumulator pairs per warp, operands in registers, no memory traffic.
+namespace {
+__global__ void dmma_probe_kernel(double *out, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmma::mma_m8n8k4(c[i][0], c[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" int qlb_fp64_tensor_peak_probe(double *tflops) {
+  Engine &e = engine();
+  if (!e.ready) return QLB_ERR_STATE;
+  QLB_CUDA(cudaSetDevice(e.device));
+  const int blocks = e.sm_count * 8, threads = 256, iters = 1 << 13;
+  double *d = nullptr;
+  QLB_CUDA(cudaMalloc((void **)&d, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  dmma_probe_kernel<<<blocks, threads, 0, e.stream>>>(d, 256);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(a, e.stream);
+    dmma_probe_kernel<<<blocks, threads, 0, e.stream>>>(d, iters);
+    cudaEventRecord(b, e.stream);
+    QLB_CUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    // one m8n8k4 = 8*8*4 FMAs = 512 flops per warp
+    const double fl = 512.0 * 8.0 * (double)iters * blocks * (threads / 32);
+    best = std::max(best, fl / (ms * 1e-3) * 1e-12);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  if (tflops) *tflops = best;
+  return QLB_OK;
+}

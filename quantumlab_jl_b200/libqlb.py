@@ -67,7 +67,7 @@ EXPORTS = (
     "qlb_set_profiling", "qlb_fp64_peak_probe", "qlb_ri_create", "qlb_ri_destroy", "qlb_ri_naux", "qlb_ri_b_tensor",
     "qlb_ri_eri_tensor", "qlb_ri_build_jk", "qlb_schedule_pieces", "qlb_qlog",
     "qlb_scf_create", "qlb_scf_destroy", "qlb_scf_set_density", "qlb_scf_build", "qlb_scf_step", "qlb_scf_get",
-    "qlb_dgemm_device", "qlb_debug_set_schedule_feedback", "qlb_tensor_contract", "qlb_ri_slice", "qlb_ri_build_jk_occ",
+    "qlb_dgemm_device", "qlb_debug_set_schedule_feedback", "qlb_tensor_contract", "qlb_ri_slice", "qlb_ri_build_jk_occ", "qlb_fp64_tensor_peak_probe",
     "qlb_multi_create", "qlb_multi_destroy", "qlb_multi_ngpu", "qlb_multi_basis0", "qlb_multi_build_jk", "qlb_multi_fock",
 )
 
@@ -135,6 +135,7 @@ def load():
     proto("qlb_multi_basis0", [C.c_void_p, C.POINTER(C.c_void_p)])
     proto("qlb_multi_build_jk", [C.c_void_p, _dp, C.c_double, _dp, _dp, C.POINTER(Stats)])
     proto("qlb_multi_fock", [C.c_void_p, _dp, _dp, C.c_double, _dp, C.POINTER(Stats)])
+    proto("qlb_fp64_tensor_peak_probe", [_dp])
     proto("qlb_ri_slice", [C.c_void_p, _ip, _ip])
     proto("qlb_ri_build_jk_occ", [C.c_void_p, _dp, C.c_int, _dp, _dp, _dp])
     proto("qlb_tensor_contract", [C.c_int, _dp, _dp, C.c_int, _dp])
@@ -180,6 +181,13 @@ def device_info():
     sm, ma, mi = C.c_int32(), C.c_int32(), C.c_int32()
     check(lib.qlb_device_info(name, 128, C.byref(sm), C.byref(ma), C.byref(mi)))
     return {"name": name.value.decode(), "sm_count": sm.value, "cc": (ma.value, mi.value)}
+
+
+def fp64_tensor_peak_probe() -> float:
+    lib = init()
+    v = C.c_double()
+    check(lib.qlb_fp64_tensor_peak_probe(C.byref(v)))
+    return v.value
 
 
 def fp64_peak_probe() -> float:

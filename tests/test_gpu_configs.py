@@ -243,3 +243,48 @@ def test_single_process_multi_gpu_matches_single_gpu(orc, qlb):
     assert np.abs(multi.fock(H, P, tau=TAU) - (H + 2 * J1 - K1)).max() < 1e-11
     multi.destroy()
     one.destroy()
+
+
+def test_function_list_entry_points(orc, qlb):
+    """a3 / a6 / a12 / a16: the basis-function flavours of the reference API on the device path -- the scalar
+    computeElectronRepulsionIntegral over four primitive / four contracted functions (IntegralsModule.jl:412-462), the
+    CGBF-vector block form (:464-470), GaussianBasis tensor, J/K and one-electron matrices, and the stored-tensor flavour of
+    J/K (SpecialMatricesModule.jl:227-229, 264-266) contracted on the device."""
+    from quantumlab_jl_b200.basisfunctions import GaussianBasis, PrimitiveGaussianBasisFunction, computeBasis
+    from quantumlab_jl_b200.basisset import loadBasisSet
+    from quantumlab_jl_b200.base import MQuantumNumber
+    from quantumlab_jl_b200.integrals import (computeElectronRepulsionIntegral, computeTensorBlockElectronRepulsionIntegrals,
+                                              computeTensorElectronRepulsionIntegrals)
+    from quantumlab_jl_b200.specialmatrices import (computeMatrixCoulomb, computeMatrixExchange, computeMatrixFock,
+                                                    computeMatrixOverlap)
+
+    geo, shells, b, nocc = make_basis(orc, "h2o_631gs")
+    ref = orc.eri_tensor(b, literal=False)  # Cook closed form, exact Boys, functions = expandShell of the shells
+    bas = GaussianBasis.from_shells(shells)  # convert(GaussianBasis, shells)
+    T = computeTensorElectronRepulsionIntegrals(bas)
+    assert np.abs(T - ref).max() < 1e-10
+    f = bas.contractedBFs
+    for (i, j, k, l) in [(0, 1, 2, 3), (13, 7, 5, 18), (16, 16, 14, 2), (4, 9, 9, 4)]:  # s, p and d functions (d_xy included)
+        assert abs(computeElectronRepulsionIntegral(f[i], f[j], f[k], f[l]) - ref[i, j, k, l]) < 1e-10
+    blk = computeTensorBlockElectronRepulsionIntegrals(f[13:19], f[0:1], f[2:5], f[13:19])  # CGBF-vector form
+    assert np.abs(blk - ref[13:19, 0:1, 2:5, 13:19]).max() < 1e-10
+    # four primitives: (mu nu|la si) of un-normalised primitives == oracle's primitive Cook formula
+    pr = [PrimitiveGaussianBasisFunction(shells[1].center, 1.3, MQuantumNumber(1, 0, 0)),
+          PrimitiveGaussianBasisFunction(shells[0].center, 0.7, MQuantumNumber(0, 0, 0)),
+          PrimitiveGaussianBasisFunction(shells[1].center, 0.9, MQuantumNumber(0, 1, 1)),
+          PrimitiveGaussianBasisFunction(shells[-1].center, 2.1, MQuantumNumber(1, 0, 0))]
+    want = orc.eri_prim([p.center for p in pr], [p.exponent for p in pr], [tuple(p.mqn) for p in pr], mode=orc.BOYS_EXACT, literal=False)
+    assert abs(computeElectronRepulsionIntegral(*pr) - want) < 1e-10 * max(1.0, abs(want))
+    # GaussianBasis flavour of J / K / S; computeBasis normalises every function by its own self-overlap
+    P = _synthetic_density(shells, seed=9)
+    J, K = orc.coulomb_from_tensor(ref, P), orc.exchange_from_tensor(ref, P)
+    assert np.abs(computeMatrixCoulomb(bas, P) - J).max() < 1e-10 and np.abs(computeMatrixExchange(bas, P) - K).max() < 1e-10
+    bas2 = computeBasis(loadBasisSet("6-31g*"), geo)
+    S2 = computeMatrixOverlap(bas2)
+    assert np.abs(np.diag(S2) - 1.0).max() < 1e-12
+    assert np.abs(computeMatrixCoulomb(bas2, P) - J).max() < 1e-10  # the two normalisation routes agree (SURVEY a6)
+    # stored-tensor flavour: contracted on the device, not with numpy
+    assert np.abs(computeMatrixCoulomb(T, P) - J).max() < 1e-11 and np.abs(computeMatrixExchange(T, P) - K).max() < 1e-11
+    F3 = computeMatrixFock(shells, geo, P)
+    F5 = computeMatrixFock(shells, geo, P, T, T)
+    assert np.abs(F3 - F5).max() < 1e-9

@@ -88,3 +88,31 @@ def test_shell_constructor_contract():
     geo = parseGeometryXYZ(["1", "", "O 0 0 0"])
     shells = computeBasisShells(BasisSetTX93(TX93), geo)
     assert [s.lqn.symbol for s in shells] == ["S", "S", "P"]
+
+
+def test_function_lists_regroup_into_device_shells():
+    """a3 / a6: basis-function lists (expandShell, computeBasis) regroup into exactly the shells of computeBasisShells; any
+    other list becomes one shell per function with the right component and scale (basisfunctions.py)."""
+    import numpy as np
+
+    from quantumlab_jl_b200 import workloads
+    from quantumlab_jl_b200.basisfunctions import FunctionMap, GaussianBasis, computeBasis, expandShell, identityCGF
+    from quantumlab_jl_b200.basisset import loadBasisSet
+    from quantumlab_jl_b200.shell import nbf
+
+    geo, shells, nocc = workloads.build("h2o_631gs")
+    bas = GaussianBasis.from_shells(shells)
+    assert len(bas) == sum(nbf(s) for s in shells) == 19
+    fm = FunctionMap(bas.contractedBFs)
+    assert len(fm.shells) == len(shells) and np.allclose(fm.scale, 1.0) and list(fm.index) == list(range(19))
+    dsh = [s for s in shells if s.lqn.exponent == 2][0]
+    d = expandShell(dsh)  # the oxygen d shell: xy, xz, yz carry sqrt(3)
+    assert np.isclose(d[1].coefficients[0] / d[0].coefficients[0], np.sqrt(3.0))
+    bas2 = computeBasis(loadBasisSet("6-31g*"), geo)
+    fm2 = FunctionMap(bas2.contractedBFs)
+    assert len(fm2.shells) == len(shells) and np.allclose(fm2.scale, 1.0, rtol=1e-12)
+    # an arbitrary pick of functions: one device shell each, the picked component, scale 1/nonaxial
+    pick = [bas.contractedBFs[i] for i in (0, 5, 16, 14)]
+    fm3 = FunctionMap(pick)
+    assert len(fm3.shells) == 4
+    assert identityCGF.primitiveBFs[0].exponent == 0.0 and identityCGF.coefficients == [1.0]
