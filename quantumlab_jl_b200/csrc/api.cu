@@ -36,7 +36,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 
 // ------------------------------------------------------------------ Boys table (host, long double series)
 static void make_boys_table(std::vector<double> &tab) {
-  // layout [L][row][BOYS_ROWLEN]: F_L..F_{L+7}(T_i), exp(-T_i), pad   (md_core.cuh)
+  // layout [L][row][BOYS_ROWLEN]: F_{L+k}(T_i)/k! (k = 0..7), exp(-T_i), pad   (md_core.cuh)
   tab.assign((size_t)(BOYS_LMAX + 1) * BOYS_TABLE_DOUBLES, 0.0);
   const int mtop = BOYS_LMAX + 7;
   std::vector<long double> F(mtop + 1);
@@ -54,7 +54,11 @@ static void make_boys_table(std::vector<double> &tab) {
     for (int m = mtop; m > 0; --m) F[m - 1] = (2.0L * T * F[m] + ex) / (2 * m - 1);
     for (int L = 0; L <= BOYS_LMAX; ++L) {
       double *row = tab.data() + (size_t)L * BOYS_TABLE_DOUBLES + (size_t)i * BOYS_ROWLEN;
-      for (int k = 0; k < 8; ++k) row[k] = (double)F[L + k];
+      long double fact = 1.0L;
+      for (int k = 0; k < 8; ++k) {
+        row[k] = (double)(F[L + k] / fact);
+        fact *= (long double)(k + 1);
+      }
       row[8] = (double)ex;
     }
   }

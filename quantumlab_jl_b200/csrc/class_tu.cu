@@ -4,6 +4,7 @@
 //                                           0 rolled loops over local-memory arrays
 //                                           1 fully unrolled, register resident, one thread per quartet (x ket-d component)
 //                                           2 cooperative (eri_coop.cuh): ncart(LC) threads per quartet, R_tuv in shared memory
+//                                           3 light (total L <= 2): as 1 with the bra primitives and E^ab staged in shared memory
 //   -DQC_DSTEP=n                          ket-d components accumulated per pass (ncart(LD) = single pass)
 //   -DQC_MINB=n                           minimum resident CTAs per SM (register cap)
 //   -DQC_CPT=n                            cooperative flavour: ket-c components per thread (warps per CTA = ncart(LC)/n)
@@ -106,6 +107,10 @@ int QC_CAT(QC_LA, QC_LB, QC_LC, QC_LD)(int mode, unsigned grid, cudaStream_t s, 
     return rc;
 #elif QC_UNR == 2
     return launch_coop<0>(grid, s, prm);
+#elif QC_UNR == 3
+    // light flavour (bra primitives staged in shared memory, ket primitive loop outside)
+    if (mode == 0) unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, ncart(QC_LD), -1, QC_MINB, false, true><<<grid, block, QC_DLSMEM(prm), s>>>(prm);
+    else unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, ncart(QC_LD), -1, QC_MINB, false, true><<<grid, block, 0, s>>>(prm);
 #elif QC_UNR
     if (mode == 0) unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 0, QC_DSTEP, -1, QC_MINB><<<grid, block, QC_DLSMEM(prm), s>>>(prm);
     else unr::eri_class_kernel<QC_LA, QC_LB, QC_LC, QC_LD, 1, QC_DSTEP, -1, QC_MINB><<<grid, block, 0, s>>>(prm);

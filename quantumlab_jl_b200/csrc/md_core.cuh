@@ -26,9 +26,9 @@ __host__ __device__ constexpr int hidx(int L, int t, int u, int v) {
 
 // ------------------------------------------------------------------ Boys function
 // One table per total angular momentum L (a class kernel needs exactly one): rows T_i = i*BOYS_DT, each row
-// {F_L(T_i) .. F_{L+7}(T_i), exp(-T_i), pad} = 80 B, read as 16-byte vectors.  29 KB per L: the class kernels keep
-// their table in shared memory (ncu: with the table in global memory the low classes were bound by L1 wavefronts,
-// every lane touching its own row).  F_L(T) by an 8-term Taylor expansion about the nearest row, lower orders by
+// {F_{L+k}(T_i)/k!, k = 0..7, exp(-T_i), pad} = 80 B, read as 16-byte vectors.  29 KB per L, L1 resident (a shared-memory
+// copy was measured slower: the carve-out shrinks L1 for the scattered pair-record / density loads).
+// F_L(T) by an 8-term Taylor expansion about the nearest row, lower orders by
 // downward recursion with exp(-T) = exp(-T_i) * poly(T_i - T); beyond the table the asymptotic F_0 and upward
 // recursion (without the exp(-T) term, which is below rounding there).  Accurate to ~2e-15 relative.
 constexpr int BOYS_ROWLEN = 10;
@@ -38,29 +38,35 @@ constexpr double BOYS_TMAX = 36.0;
 constexpr int BOYS_NROW = 362;          // rows 0..361 (T up to 36.1)
 constexpr int BOYS_TABLE_DOUBLES = BOYS_NROW * BOYS_ROWLEN;
 
-// tab: the table of THIS L (global or shared memory)
+// tab: the table of THIS L.  Rows hold the Taylor coefficients F_{L+k}(T_i)/k! (k = 0..7) so that the expansion is a bare
+// Horner chain (ncu round 2: the seven d/k multiplications were a third of the FP64 instructions of the table path).
+template <int L>
+__device__ __forceinline__ void boys_table(double T, const double *tab, double *F) {
+  const int i = (int)(T * (1.0 / BOYS_DT) + 0.5);
+  const double d = (double)i * BOYS_DT - T;  // T_i - T, |d| <= DT/2
+  const double2 *row = reinterpret_cast<const double2 *>(tab + i * BOYS_ROWLEN);
+  const double2 r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2), r3 = __ldg(row + 3);
+  double f = r3.y;
+  f = fma(f, d, r3.x); f = fma(f, d, r2.y); f = fma(f, d, r2.x);
+  f = fma(f, d, r1.y); f = fma(f, d, r1.x); f = fma(f, d, r0.y);
+  f = fma(f, d, r0.x);
+  F[L] = f;
+  if (L > 0) {
+    // exp(-T) = exp(-T_i) * exp(d): tabulated exp(-T_i) times a degree-8 Taylor polynomial (|d| <= 0.05)
+    double e = 1.0 / 40320.0;
+    e = fma(e, d, 1.0 / 5040.0); e = fma(e, d, 1.0 / 720.0); e = fma(e, d, 1.0 / 120.0); e = fma(e, d, 1.0 / 24.0);
+    e = fma(e, d, 1.0 / 6.0); e = fma(e, d, 0.5); e = fma(e, d, 1.0); e = fma(e, d, 1.0);
+    e *= __ldg(row + 4).x;
+    const double t2 = 2.0 * T;
+#pragma unroll
+    for (int m = L; m >= 1; --m) F[m - 1] = fma(t2, F[m], e) * (1.0 / (2 * m - 1));
+  }
+}
+
 template <int L>
 __device__ __forceinline__ void boys_array(double T, const double *tab, double *F) {
   if (T < BOYS_TMAX) {
-    const int i = (int)(T * (1.0 / BOYS_DT) + 0.5);
-    const double d = (double)i * BOYS_DT - T;  // T_i - T, |d| <= DT/2
-    const double2 *row = reinterpret_cast<const double2 *>(tab + i * BOYS_ROWLEN);
-    const double2 r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2), r3 = __ldg(row + 3);
-    double f = r3.y;
-    f = fma(f, d * (1.0 / 7), r3.x); f = fma(f, d * (1.0 / 6), r2.y); f = fma(f, d * (1.0 / 5), r2.x);
-    f = fma(f, d * (1.0 / 4), r1.y); f = fma(f, d * (1.0 / 3), r1.x); f = fma(f, d * (1.0 / 2), r0.y);
-    f = fma(f, d, r0.x);
-    F[L] = f;
-    if (L > 0) {
-      // exp(-T) = exp(-T_i) * exp(d): tabulated exp(-T_i) times a degree-8 Taylor polynomial (|d| <= 0.05)
-      double e = 1.0 / 40320.0;
-      e = fma(e, d, 1.0 / 5040.0); e = fma(e, d, 1.0 / 720.0); e = fma(e, d, 1.0 / 120.0); e = fma(e, d, 1.0 / 24.0);
-      e = fma(e, d, 1.0 / 6.0); e = fma(e, d, 0.5); e = fma(e, d, 1.0); e = fma(e, d, 1.0);
-      e *= __ldg(row + 4).x;
-      const double t2 = 2.0 * T;
-#pragma unroll
-      for (int m = L; m >= 1; --m) F[m - 1] = fma(t2, F[m], e) * (1.0 / (2 * m - 1));
-    }
+    boys_table<L>(T, tab, F);
   } else if constexpr (L <= 2) {
     // T >= 36, low orders: F_0 = sqrt(pi/T)/2 and the upward recursion WITHOUT its exp(-T) term: exp(-36) = 2.3e-16 is
     // below the rounding error of the terms it is added to (relative 1.6e-15 for F_1, 4e-14 for F_2 at T = 36, smaller

@@ -19,7 +19,7 @@ __device__ static void boys_rt(int L, double T, const double *__restrict__ tab, 
     const double d = (double)i * BOYS_DT - T;
     const double *row = tab + (size_t)L * BOYS_TABLE_DOUBLES + i * BOYS_ROWLEN;
     double f = row[7];
-    for (int k = 6; k >= 0; --k) f = fma(f, d / (k + 1), row[k]);
+    for (int k = 6; k >= 0; --k) f = fma(f, d, row[k]);  // rows hold F_{L+k}/k!
     F[L] = f;
     for (int m = L; m >= 1; --m) F[m - 1] = (2.0 * T * F[m] + e) / (2 * m - 1);
   } else {
