@@ -201,6 +201,10 @@ int qlb_scf_get(qlb_scf *s, int what, double *out);
  * kernel (mma.sync m8n8k4 f64 = DMMA): the contraction engine of qlb_scf_step and of the RI path; exported for tests. */
 int qlb_dgemm_device(int transA, int transB, int M, int N, int K, double alpha, const double *dA, int lda, const double *dB,
                      int ldb, double beta, double *dC, int ldc, void *stream);
+/* The packed-symmetric products of the RI-K contraction (ResolutionIdentityModule.jl:69-78) on DEVICE pointers, exported
+ * for tests: dBp = nslab packed lower triangles (column-major, N(N+1)/2 each).  side 0: X[:,:,q] = B^q R (R N x ncol);
+ * side 1: out = sum_q X[:,:,q] B^q (R = X, N x N x nslab). */
+int qlb_dsymm_packed_device(int side, int N, int ncol, int nslab, const double *dBp, const double *dR, double *dOut, void *stream);
 
 /* ---- knobs ---------------------------------------------------------------------------------------------- */
 int qlb_qlog(double x);        /* the integer screening rule's qlog(x) = ceil(8 log2 x), exact table form (tests) */

@@ -279,6 +279,30 @@ extern "C" int qlb_dgemm_device(int ta, int tb, int M, int N, int K, double alph
   return QLB_OK;
 }
 
+// The two packed-symmetric products of the RI-K contraction on DEVICE pointers (tests): Bp = nslab packed lower triangles
+// (column-major, N(N+1)/2 doubles each).
+//   side 0:  X[:, :, q] = B^q R            R: N x ncol,          X: N x ncol x nslab
+//   side 1:  Kout = sum_q X[:, :, q] B^q   X: N x N x nslab,     Kout: N x N
+extern "C" int qlb_dsymm_packed_device(int side, int N, int ncol, int nslab, const double *dBp, const double *dR, double *dOut, void *stream_) {
+  Engine &e = engine();
+  if (!e.ready) return QLB_ERR_STATE;
+  if (N <= 0 || nslab <= 0 || !dBp || !dR || !dOut) {
+    set_error("qlb_dsymm_packed_device: bad argument");
+    return QLB_ERR_ARG;
+  }
+  cudaStream_t st = stream_ ? (cudaStream_t)stream_ : e.stream;
+  const int64_t NP = (int64_t)N * (N + 1) / 2;
+  cudaError_t ce;
+  if (side == 0)
+    ce = dmma::dgemm_ex(st, N, ncol, N, 1.0, {dBp, NP, dmma::LAY_SYM, NP}, {dR, (int64_t)N, dmma::LAY_K, 0}, 0.0, dOut, (int64_t)N,
+                        (int64_t)N * ncol, nslab, false, N);
+  else
+    ce = dmma::dgemm_ex(st, N, N, N * nslab, 1.0, {dR, (int64_t)N, dmma::LAY_MN, 0}, {dBp, NP, dmma::LAY_SYM, 0}, 0.0, dOut, (int64_t)N, 0, 1,
+                        false, N);
+  if (ce != cudaSuccess) return cuda_fail(ce, "dsymm_packed");
+  return QLB_OK;
+}
+
 // DMMA microbenchmark: the measured FP64 tensor-core roofline denominator of the RI contractions.  8 independent
 // accumulator pairs per warp, operands in registers, no memory traffic.
 namespace {

@@ -67,7 +67,7 @@ EXPORTS = (
     "qlb_set_profiling", "qlb_fp64_peak_probe", "qlb_ri_create", "qlb_ri_destroy", "qlb_ri_naux", "qlb_ri_b_tensor",
     "qlb_ri_eri_tensor", "qlb_ri_build_jk", "qlb_schedule_pieces", "qlb_qlog",
     "qlb_scf_create", "qlb_scf_destroy", "qlb_scf_set_density", "qlb_scf_build", "qlb_scf_step", "qlb_scf_get",
-    "qlb_dgemm_device", "qlb_debug_set_schedule_feedback", "qlb_tensor_contract", "qlb_ri_slice", "qlb_ri_build_jk_occ", "qlb_fp64_tensor_peak_probe",
+    "qlb_dgemm_device", "qlb_dsymm_packed_device", "qlb_debug_set_schedule_feedback", "qlb_tensor_contract", "qlb_ri_slice", "qlb_ri_build_jk_occ", "qlb_fp64_tensor_peak_probe",
     "qlb_multi_create", "qlb_multi_destroy", "qlb_multi_ngpu", "qlb_multi_basis0", "qlb_multi_build_jk", "qlb_multi_fock",
 )
 
@@ -140,6 +140,7 @@ def load():
     proto("qlb_ri_build_jk_occ", [C.c_void_p, _dp, C.c_int, _dp, _dp, _dp])
     proto("qlb_tensor_contract", [C.c_int, _dp, _dp, C.c_int, _dp])
     proto("qlb_debug_set_schedule_feedback", [C.c_void_p, C.c_int, _dp, _dp])
+    proto("qlb_dsymm_packed_device", [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
     proto("qlb_dgemm_device", [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p])
     _lib = lib
     return lib

@@ -202,7 +202,12 @@ def test_device_scf_matches_host_loop(orc, qlb, name):
 
 
 @pytest.mark.parametrize("ta,tb,M,N,K", [(0, 0, 64, 64, 16), (0, 1, 200, 200, 37), (1, 0, 130, 67, 301), (1, 1, 33, 129, 5),
-                                         (0, 1, 608, 608, 160), (0, 0, 1, 1, 1)])
+                                         (0, 1, 608, 608, 160), (0, 0, 1, 1, 1),
+                                         # the 128 x 128 / 128 x 64 tile kernels, every layout pair, ragged edges
+                                         (0, 0, 256, 192, 100), (0, 1, 300, 130, 77), (1, 0, 130, 260, 301), (1, 1, 257, 129, 50),
+                                         (0, 0, 400, 160, 33), (1, 1, 128, 64, 16),
+                                         # split-K (few tiles, long contraction index)
+                                         (0, 1, 130, 130, 4000), (1, 0, 64, 60, 3000), (0, 0, 300, 200, 1111)])
 def test_dmma_gemm_matches_numpy(qlb, ta, tb, M, N, K):
     import torch
 
@@ -220,6 +225,33 @@ def test_dmma_gemm_matches_numpy(qlb, ta, tb, M, N, K):
     torch.cuda.synchronize()
     got = dC.cpu().numpy().T
     assert np.abs(got - ref).max() < 1e-12 * max(1, K)
+
+
+@pytest.mark.parametrize("N,ncol,nslab", [(20, 7, 3), (200, 130, 3), (150, 64, 2), (131, 131, 1)])
+def test_dmma_packed_symmetric_products(qlb, N, ncol, nslab):
+    """LAY_SYM operand of the DMMA kernels (small and large tiles): X^q = B^q R and K = sum_q X^q B^q against numpy."""
+    import torch
+
+    lib = qlb.load()
+    rng = np.random.default_rng(N + ncol)
+    Bs = rng.standard_normal((nslab, N, N))
+    Bs = Bs + Bs.transpose(0, 2, 1)
+    packed = np.concatenate([np.concatenate([Bs[q][b:, b] for b in range(N)]) for q in range(nslab)])
+    R = rng.standard_normal((N, ncol))
+    dB = torch.tensor(packed, dtype=torch.float64, device="cuda")
+    dR = torch.tensor(R.T.copy(), dtype=torch.float64, device="cuda")
+    dX = torch.zeros(nslab * ncol * N, dtype=torch.float64, device="cuda")
+    qlb.check(lib.qlb_dsymm_packed_device(0, N, ncol, nslab, C.c_void_p(dB.data_ptr()), C.c_void_p(dR.data_ptr()), C.c_void_p(dX.data_ptr()), None))
+    torch.cuda.synchronize()
+    X = dX.cpu().numpy().reshape(nslab, ncol, N).transpose(0, 2, 1)
+    assert np.abs(X - Bs @ R).max() < 1e-12 * N
+    Y = rng.standard_normal((nslab, N, N))
+    dY = torch.tensor(Y.transpose(0, 2, 1).copy(), dtype=torch.float64, device="cuda")
+    dK = torch.zeros(N * N, dtype=torch.float64, device="cuda")
+    qlb.check(lib.qlb_dsymm_packed_device(1, N, N, nslab, C.c_void_p(dB.data_ptr()), C.c_void_p(dY.data_ptr()), C.c_void_p(dK.data_ptr()), None))
+    torch.cuda.synchronize()
+    K = dK.cpu().numpy().reshape(N, N).T
+    assert np.abs(K - sum(Y[q] @ Bs[q] for q in range(nslab))).max() < 1e-12 * N * nslab
 
 
 def test_single_process_multi_gpu_matches_single_gpu(orc, qlb):
