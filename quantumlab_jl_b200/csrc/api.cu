@@ -1233,16 +1233,11 @@ int qlb::allreduce_sum_device(double *d, size_t n, cudaStream_t s) {
   return QLB_OK;
 }
 
-extern "C" int qlb_allreduce_jk_device(qlb_basis *b, double *dJK, void *stream_) {
-  if (int rc = enter(b)) return rc;
-  Engine &e = g_engine;
-  if (!b || !dJK) return QLB_ERR_ARG;
-  if (!e.nccl_comm) {
-    set_error("qlb_allreduce_jk_device: no communicator (qlb_comm_init)");
-    return QLB_ERR_STATE;
-  }
+// The all-reduce of [J;K] + schedule feedback in three stream-ordered parts, so that the single-process front end can
+// put the collectives of all its devices into one NCCL group (inside a group the collective is only enqueued at
+// ncclGroupEnd: anything that must follow it on the stream has to be issued after the group).
+static int allreduce_jk_pre(qlb_basis *b, double *dJK, cudaStream_t s) {
   static_assert(3 * NQCLASS <= QLB_JK_TAIL, "QLB_JK_TAIL too small");
-  cudaStream_t s = stream_ ? (cudaStream_t)stream_ : e.stream;
   const size_t n = 2 * (size_t)b->nbf * b->nbf;
   // schedule feedback rides behind [J;K]: ONE collective per build
   const double *dms = nullptr;
@@ -1252,13 +1247,36 @@ extern "C" int qlb_allreduce_jk_device(qlb_basis *b, double *dJK, void *stream_)
     b->ms_local_pending = false;
   }
   jk_tail_kernel<<<1, QLB_JK_TAIL, 0, s>>>(b->d_counters, dms, dJK + n);
-  ncclResult_t r = p_AllReduce(dJK, dJK, n + QLB_JK_TAIL, ncclDouble, ncclSum, (ncclComm_t)e.nccl_comm, s);
+  QLB_CUDA(cudaGetLastError());
+  return QLB_OK;
+}
+static int allreduce_jk_reduce(qlb_basis *b, double *dJK, cudaStream_t s) {
+  const size_t n = 2 * (size_t)b->nbf * b->nbf;
+  ncclResult_t r = p_AllReduce(dJK, dJK, n + QLB_JK_TAIL, ncclDouble, ncclSum, (ncclComm_t)g_engine.nccl_comm, s);
   if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce");
+  return QLB_OK;
+}
+static int allreduce_jk_post(qlb_basis *b, double *dJK, cudaStream_t s) {
+  const size_t n = 2 * (size_t)b->nbf * b->nbf;
   QLB_CUDA(cudaMemcpyAsync(b->h_gcounts, dJK + n, 3 * NQCLASS * sizeof(double), cudaMemcpyDeviceToHost, s));
   QLB_CUDA(cudaEventRecord(b->ev_gcounts, s));
   b->gcounts_pending = true;
-  b->gcounts_nranks = e.nranks;
+  b->gcounts_nranks = g_engine.nranks;
   return QLB_OK;
+}
+
+extern "C" int qlb_allreduce_jk_device(qlb_basis *b, double *dJK, void *stream_) {
+  if (int rc = enter(b)) return rc;
+  Engine &e = g_engine;
+  if (!b || !dJK) return QLB_ERR_ARG;
+  if (!e.nccl_comm) {
+    set_error("qlb_allreduce_jk_device: no communicator (qlb_comm_init)");
+    return QLB_ERR_STATE;
+  }
+  cudaStream_t s = stream_ ? (cudaStream_t)stream_ : e.stream;
+  if (int rc = allreduce_jk_pre(b, dJK, s)) return rc;
+  if (int rc = allreduce_jk_reduce(b, dJK, s)) return rc;
+  return allreduce_jk_post(b, dJK, s);
 }
 
 // =================================================================== single process, several devices
@@ -1368,15 +1386,24 @@ static int multi_build(qlb_multi *m, const double *H, const double *P, double ta
     if (int rc = qlb_build_jk_device(b, b->d_P, tau, b->d_JK, b->d_JK + N2, d, n, nullptr, d == 0 ? stats : nullptr)) return rc;
   }
   if (n > 1) {
+    for (int d = 0; d < n; ++d) {
+      use_engine(&g_engines[d]);
+      if (int rc = allreduce_jk_pre(m->basis[d], m->basis[d]->d_JK, g_engines[d].stream)) return rc;
+    }
     p_GroupStart();
     for (int d = 0; d < n; ++d) {
-      if (int rc = qlb_allreduce_jk_device(m->basis[d], m->basis[d]->d_JK, nullptr)) {
+      use_engine(&g_engines[d]);
+      if (int rc = allreduce_jk_reduce(m->basis[d], m->basis[d]->d_JK, g_engines[d].stream)) {
         p_GroupEnd();
         return rc;
       }
     }
     ncclResult_t r = p_GroupEnd();
     if (r != ncclSuccess) return nccl_fail(r, "ncclGroupEnd(all-reduce)");
+    for (int d = 0; d < n; ++d) {  // after the group: the collective is on the streams now
+      use_engine(&g_engines[d]);
+      if (int rc = allreduce_jk_post(m->basis[d], m->basis[d]->d_JK, g_engines[d].stream)) return rc;
+    }
   }
   use_engine(&g_engines[0]);
   Engine &e = g_engines[0];

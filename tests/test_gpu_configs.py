@@ -268,9 +268,9 @@ def test_single_process_multi_gpu_matches_single_gpu(orc, qlb):
     one = B200Shells(shells)
     J1, K1 = one.build_jk(P, tau=TAU)
     multi = B200MultiShells(shells, ngpu)
-    for _ in range(3):  # calibration build, first scheduled build, steady state
+    for it in range(4):  # calibration build, first scheduled build, steady state
         J, K = multi.build_jk(P, tau=TAU)
-        assert np.abs(J - J1).max() < 1e-12 and np.abs(K - K1).max() < 1e-12
+        assert np.abs(J - J1).max() < 1e-12 and np.abs(K - K1).max() < 1e-12, f"build {it}"
     H = one.one_electron("kinetic") + one.one_electron("nuclear", geo)
     assert np.abs(multi.fock(H, P, tau=TAU) - (H + 2 * J1 - K1)).max() < 1e-11
     multi.destroy()
