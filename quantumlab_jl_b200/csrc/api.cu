@@ -669,25 +669,35 @@ static void base_params(qlb_basis *b, ClassParams &prm) {
   prm.nranks = 1;
 }
 
-// Dealing class pieces to ranks.  cost[qc] is the MEASURED cost of class pair qc (class kernel time of the calibration
-// build summed over the ranks, scaled by the class's current work): no compiled-in efficiency table.  Every class pair
-// is cut into 1..nranks pieces of about a third of a rank's share and the pieces are assigned longest-first to the least
-// loaded rank.  Pure function of (cost, nranks): identical on all ranks.
+// Dealing class pieces to ranks.  cost[qc] is the MEASURED cost (ms) of class pair qc (class kernel time of the calibration
+// build summed over the ranks, scaled by the class's current work): no compiled-in efficiency table.
+//  * A class whose per-rank share is at least SPLIT_MIN_MS is cut into nranks pieces (row subsets p, p+nranks, ... of the
+//    bound-sorted rows), one per rank: balanced by construction.  (Measured on 2 GPUs, (H2O)32: dealing whole classes
+//    longest-first by their calibration times gave 20.1 ms per build, dealing rows 18.3 ms -- class times measured one
+//    kernel at a time do not add up under concurrent streams.)
+//  * Smaller classes would become launch/tail-bound slivers: they are cut into pieces of about SPLIT_MIN_MS and the pieces
+//    assigned longest-first to the least loaded rank.
+// Pure function of (cost, nranks): identical on all ranks.
+constexpr double SPLIT_MIN_MS = 0.12;
 static bool build_schedule(const double *cost, int rank, int nranks, std::vector<std::pair<int, int>> *mine) {
   double total = 0.0;
   for (int qc = 0; qc < NQCLASS; ++qc) total += std::max(cost[qc], 0.0);
   if (!(total > 0.0)) return false;
   struct Piece { double c; int qc, p, np; };
   std::vector<Piece> pieces;
-  const double target = total / (3.0 * nranks);
+  std::vector<double> load(nranks, 0.0);
   for (int qc = 0; qc < NQCLASS; ++qc) {
     const double c = std::max(cost[qc], 0.0);
-    int np = (int)ceil(c / target);
-    np = std::max(1, std::min(np, nranks));
+    if (c >= SPLIT_MIN_MS * nranks) {
+      // piece p goes to rank (p + qc) mod nranks: the rank that receives row 0 (the heaviest) rotates with the class
+      for (int r = 0; r < nranks; ++r) load[r] += c / nranks;
+      mine[qc].push_back({(rank + qc) % nranks, nranks});
+      continue;
+    }
+    const int np = std::max(1, std::min((int)floor(c / SPLIT_MIN_MS), nranks));
     for (int p = 0; p < np; ++p) pieces.push_back({c / np, qc, p, np});
   }
   std::stable_sort(pieces.begin(), pieces.end(), [](const Piece &a, const Piece &b) { return a.c > b.c; });
-  std::vector<double> load(nranks, 0.0);
   for (const Piece &pc : pieces) {
     int r = 0;
     for (int k = 1; k < nranks; ++k)
