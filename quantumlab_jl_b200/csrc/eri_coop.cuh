@@ -478,8 +478,9 @@ __global__ void __launch_bounds__(32 * (ncart(LC) / CPT), MINB) eri_coop_kernel(
       }
       __syncwarp();
     }
+    int mcur = 0;  // cursor of the merged drain at the end of the walk
 #pragma unroll 1
-    for (bool first = true;; first = false) {  // drain: every bucket that holds a full batch (at the end: anything)
+    for (bool first = true;; first = false) {  // drain: every bucket that holds a full batch; at the end of the walk the rest
     int ikc = ik;
     bool act = active, run = first && m != 0u;
     if (!tensor_mode) {
@@ -487,20 +488,32 @@ __global__ void __launch_bounds__(32 * (ncart(LC) / CPT), MINB) eri_coop_kernel(
 #pragma unroll
       for (int k = QUEUE_NBK - 1; k >= 0; --k) {
         const int cnt = (qn >> (8 * k)) & 0xffu;
-        if (cnt >= 32 || (last && cnt > 0)) kb = k;
+        if (cnt >= 32) kb = k;
       }
       run = kb >= 0;
       if (run) {
         const int cnt = (qn >> (8 * kb)) & 0xffu;
-        const int take = min(cnt, 32), rest = cnt - take;
+        const int rest = cnt - 32;
         int *qb = queue + 64 * kb;
-        act = lane < take;
-        ikc = act ? qb[lane] : 0;
+        act = true;
+        ikc = qb[lane];
         const int carry = (lane < rest) ? qb[32 + lane] : 0;
         __syncwarp();
         if (lane < rest) qb[lane] = carry;
-        qn -= (unsigned)take << (8 * kb);
+        qn -= 32u << (8 * kb);
         __syncwarp();
+      } else if (last) {
+        // end of the walk: the leftovers of all buckets, longest contraction first, in batches of 32 (see eri_body.inc)
+        const int c3 = (qn >> 24) & 0xffu, c2 = (qn >> 16) & 0xffu, c1 = (qn >> 8) & 0xffu, c0 = qn & 0xffu;
+        const int o3 = c3, o2 = o3 + c2, o1 = o2 + c1, total = o1 + c0;
+        run = mcur < total;
+        if (run) {
+          const int e = mcur + lane;
+          act = e < total;
+          const int src = e < o3 ? 192 + e : (e < o2 ? 128 + (e - o3) : (e < o1 ? 64 + (e - o2) : e - o1));
+          ikc = act ? queue[src] : 0;
+          mcur += 32;
+        }
       }
     }
     if (!run) break;
