@@ -758,6 +758,26 @@ extern "C" int qlb_debug_set_schedule_feedback(qlb_basis *b, int nranks, const d
 
 // policy of a class pair (class_tu.cu, mode -1): bra pairs per CTA and kernels launched per class-pair launch
 static int tile_bra_of(int X, int Y) { return launch_class_kernel(X, Y, -1, 0, nullptr, ClassParams()) & 0xff; }
+// CTAs per SM of one class launch (sizes ysplit, the CTAs per bra tile row).  A property of the class KERNEL: light classes
+// want many short walks (their batches are cheap, the GPU must be filled), the cooperative high-L classes few long ones
+// (fuller batches, the bra-side Hermite coefficients staged once per walk).  Measured per class on two unlike workloads,
+// (H2O)32/6-31G* and C40H82/def2-SVP, with scripts/shard_classes.py over 4..512 (gpurun_out r2x): the best value per class is
+// the same on both to within one step of the sweep; QLB_YS_TARGET overrides all of them.
+static int ys_target_of(int X, int Y, const Engine &e) {
+  if (e.ys_target > 0) return e.ys_target;
+  int la, lb, lc, ld;
+  class_L(X, la, lb);
+  class_L(Y, lc, ld);
+  const int L = la + lb + lc + ld;
+  if (lc + ld == 0 && lb == 0) return 64;                       // (ss|ss) (ps|ss) (ds|ss)
+  if (tile_bra_of(X, Y) == 1) {                                 // cooperative flavour
+    if (la == 2 && lb == 1 && lc == 1 && ld == 1) return 32;    // (dp|pp)
+    if (L == 5 || (la + lb == 3 && lc + ld == 3)) return 16;    // (dd|ps) (dp|dp)
+    return 8;                                                   // (dd|pp) (dd|ds) (dd|dp) (dd|dd)
+  }
+  if (L <= 3 || (la + lb == 3 && lc + ld == 1)) return 32;      // (ps|ps) (pp|ss) (pp|ps) (ds|ps) (dp|ss) (dp|ps)
+  return 16;                                                    // (pp|pp) (ds|pp) (ds|ds) (dp|ds) (dd|ss)
+}
 static int launch_count_of(int X, int Y) { return launch_class_kernel(X, Y, -1, 0, nullptr, ClassParams()) >> 8; }
 
 // number of leading pairs of segment sg (sorted by bound, descending) with ql >= need
@@ -893,7 +913,7 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       // (rows differ a lot in length), but >= 8 tiles per CTA when that still leaves >= 64 CTAs per SM, so the row's
       // bra data are read once per many tiles.  (QLB_YS_TARGET / QLB_YS_TILES / QLB_YSPLIT_FULL: tuning knobs read in
       // qlb_init; the result was insensitive to them: 65.3-65.9 ms over a 16x range.)
-      int ysplit = (int)std::min<int64_t>(nbx_eff, ((int64_t)e.sm_count * e.ys_target + nrows_local - 1) / nrows_local);
+      int ysplit = (int)std::min<int64_t>(nbx_eff, ((int64_t)e.sm_count * ys_target_of(X, Y, e) + nrows_local - 1) / nrows_local);
       const int ys_amort = std::max(1, nbx_eff / e.ys_tiles);
       if ((int64_t)nrows_local * ys_amort >= (int64_t)e.sm_count * 64) ysplit = std::min(ysplit, ys_amort);
       ysplit = std::max(1, ysplit);

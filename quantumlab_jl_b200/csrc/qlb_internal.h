@@ -37,7 +37,8 @@ struct Engine {
   // tuning knobs, read from the environment once in qlb_init
   // CTAs per SM per class launch that size ysplit.  Measured (gpurun r2v, B200): 29.3 / 30.8 / 32.7 / 34.2 ms per (H2O)32 build and
   // 79.0 / 81.7 / 84.9 / 87.1 ms per C40H82 build for 32 / 64 / 128 / 256 -- shorter walks end in more partial batches
-  int ys_target = 32, ys_tiles = 8;
+  // 0 = the per-class table ys_target_of() in api.cu (default); QLB_YS_TARGET sets one value for every class
+  int ys_target = 0, ys_tiles = 8;
   // width (in qlog units, 8 per factor 2) of the Schwarz-bound bins of the pair order; 1 = exact order of the bounds.
   // Measured on (H2O)32: wider bins (index-local tiles) LOSE -- 45.5 / 54 / 62 / 74 / 85 ms per build for 1 / 8 / 16 / 32 / 64
   int bin_width = 1;
