@@ -284,6 +284,9 @@ extern "C" int qlb_init(int device) {
   QLB_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024));
   if (const char *v = getenv("QLB_YS_TARGET")) e.ys_target = std::max(1, atoi(v));
   if (const char *v = getenv("QLB_YS_TILES")) e.ys_tiles = std::max(1, atoi(v));
+  if (const char *v = getenv("QLB_LAUNCH_ORDER")) e.launch_order = atoi(v);
+  if (const char *v = getenv("QLB_NSIDE")) e.nside = std::max(0, std::min(atoi(v), (int)Engine::NSIDE));
+  if (const char *v = getenv("QLB_DLSMEM_MIN_TILES")) e.dlsmem_min_tiles = std::max(0, atoi(v));
   e.ysplit_full = getenv("QLB_YSPLIT_FULL") != nullptr;
   if (const char *v = getenv("QLB_BIN_W")) e.bin_width = std::max(1, atoi(v));
   e.no_schedule = getenv("QLB_NO_SCHEDULE") != nullptr;
@@ -844,6 +847,7 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
   prm.tlog = tlog; prm.screen = screen ? 1 : 0;
   prm.rank = rank; prm.nranks = nranks;
   prm.P = dP; prm.J = dJ; prm.K = dK;
+  const int dl_smem_base = prm.dl_smem;
   if (stats) cudaEventRecord(b->ev[1], s);
   bool qc_started[NQCLASS] = {false};
   // ---- multi-rank schedule from measured class costs (identical on every rank)
@@ -876,8 +880,33 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
     while (sg < nseg && b->seg_cls[sg] < c) ++sg;
     cls_seg[c] = sg;
   }
-  for (int X = NCLASS - 1; X >= 0; --X)
-   for (int Y = X; Y >= 0; --Y)
+  // Launch order of the class pairs: the launches are dealt over the build stream and the side streams, and the build
+  // ends when the last kernel's last CTA does -- the classes expected to run longest go first.  Expected cost = significant
+  // bra pairs x significant ket pairs x flops per primitive quartet of the class (host-side quantities only).
+  std::vector<std::pair<int, int>> xy_order;
+  {
+    std::vector<std::pair<double, std::pair<int, int>>> keyed;
+    for (int X = NCLASS - 1; X >= 0; --X)
+      for (int Y = X; Y >= 0; --Y) {
+        double est = 0.0;
+        for (int sx = cls_seg[X]; sx < cls_seg[X + 1]; ++sx)
+          for (int sy = cls_seg[Y]; sy < cls_seg[Y + 1]; ++sy) {
+            double fp, fd;
+            class_flops(X, Y, fp, fd);
+            est += (double)sig_count(sx, dl_guess) * (double)sig_count(sy, dl_guess) * (X == Y ? 0.5 : 1.0) * (fp + fd);
+          }
+        keyed.push_back({est, {X, Y}});
+      }
+    // measured (gpurun r3f): by expected cost for a 1/8 share 4.60 -> 4.45 ms ((H2O)32), 10.80 -> 10.70 ms (C40H82); on whole
+    // builds no difference, and on benzene (every kernel latency-bound) 2.6 -> 2.9 ms: used for sharded builds only
+    const int order = e.launch_order >= 0 ? e.launch_order : (nranks > 1 ? 2 : 0);
+    if (order == 1) std::reverse(keyed.begin(), keyed.end());
+    else if (order == 2)
+      std::stable_sort(keyed.begin(), keyed.end(), [](const auto &a, const auto &c) { return a.first > c.first; });
+    for (const auto &k : keyed) xy_order.push_back(k.second);
+  }
+  for (const auto &xy : xy_order) {
+   const int X = xy.first, Y = xy.second;
     for (int sx = cls_seg[X + 1] - 1; sx >= cls_seg[X]; --sx)
      for (int sy = (X == Y ? sx : cls_seg[Y + 1] - 1); sy >= cls_seg[Y]; --sy) {
       const int qc = qclass_of(X, Y);
@@ -919,6 +948,9 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       ysplit = std::max(1, ysplit);
       if (e.ysplit_full) ysplit = nbx_eff;
       prm.ysplit = ysplit;
+      // staging the bra shells' rows of the density-bound table (2 x nsh entries per warp) pays from a handful of tiles per
+      // walk; with short walks (small systems, many ranks) the per-CTA staging cost exceeds the gathers it saves
+      prm.dl_smem = (dl_smem_base && nbx_eff / ysplit >= e.dlsmem_min_tiles) ? 1 : 0;
       const int64_t grid = (int64_t)nrows_local * ysplit;
       prm.counters = b->d_counters + 2 * qc;
       if (prof && !qc_started[qc]) cudaEventRecord(b->ev[4 + 2 * qc], s);
@@ -928,16 +960,16 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       if (!prof) {
         if (!forked) {
           QLB_CUDA(cudaEventRecord(e.ev_fork, s));
-          for (int i = 0; i < Engine::NSIDE; ++i) QLB_CUDA(cudaStreamWaitEvent(e.side_stream[i], e.ev_fork, 0));
+          for (int i = 0; i < e.nside; ++i) QLB_CUDA(cudaStreamWaitEvent(e.side_stream[i], e.ev_fork, 0));
           forked = true;
         }
-        const int which = nlaunch_classes++ % (Engine::NSIDE + 1);
+        const int which = nlaunch_classes++ % (e.nside + 1);
         if (which > 0) ls = e.side_stream[which - 1];
       }
       const int ce = launch_class_kernel(X, Y, 0, (unsigned)grid, ls, prm);
       if (ce) {
         if (forked)  // join the side streams before reporting the failure
-          for (int i = 0; i < Engine::NSIDE; ++i) {
+          for (int i = 0; i < e.nside; ++i) {
             cudaEventRecord(e.ev_join[i], e.side_stream[i]);
             cudaStreamWaitEvent(s, e.ev_join[i], 0);
           }
@@ -947,8 +979,9 @@ extern "C" int qlb_build_jk_device(qlb_basis *b, const double *dP, double tau, d
       launches += launch_count_of(X, Y);
      }  // pieces
     }
+  }  // class pairs
   if (forked)
-    for (int i = 0; i < Engine::NSIDE; ++i) {
+    for (int i = 0; i < e.nside; ++i) {
       QLB_CUDA(cudaEventRecord(e.ev_join[i], e.side_stream[i]));
       QLB_CUDA(cudaStreamWaitEvent(s, e.ev_join[i], 0));
     }

@@ -29,7 +29,8 @@ struct Engine {
   cudaStream_t stream = nullptr;
   // class kernels are independent (they only add into J/K): they are dealt over the build stream plus these side
   // streams so that the tail of one class overlaps the body of the next
-  static constexpr int NSIDE = 7;
+  static constexpr int NSIDE = 39;  // streams created; nside of them are used (QLB_NSIDE)
+  int nside = 7;
   cudaStream_t side_stream[NSIDE] = {nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {nullptr};
   double *d_boys = nullptr;
@@ -39,6 +40,8 @@ struct Engine {
   // 79.0 / 81.7 / 84.9 / 87.1 ms per C40H82 build for 32 / 64 / 128 / 256 -- shorter walks end in more partial batches
   // 0 = the per-class table ys_target_of() in api.cu (default); QLB_YS_TARGET sets one value for every class
   int ys_target = 0, ys_tiles = 8;
+  int dlsmem_min_tiles = 12;
+  int launch_order = -1;  // class launch order: 0 high L first, 1 low L first, 2 expected cost descending, -1 auto (QLB_LAUNCH_ORDER)  // ket tiles per walk from which the kernels stage the density-bound rows in shared memory
   // width (in qlog units, 8 per factor 2) of the Schwarz-bound bins of the pair order; 1 = exact order of the bounds.
   // Measured on (H2O)32: wider bins (index-local tiles) LOSE -- 45.5 / 54 / 62 / 74 / 85 ms per build for 1 / 8 / 16 / 32 / 64
   int bin_width = 1;

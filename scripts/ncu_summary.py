@@ -1,40 +1,77 @@
-"""Summarise ncu reports (raw page) into a compact table.  usage: ncu_summary.py tag:file ..."""
-import csv, io, subprocess, sys
-WANT = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__occupancy_limit_registers',
-        'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
-        'smsp__thread_inst_executed_per_inst_executed.ratio', 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
-        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
-        'l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
-        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
-        'lts__t_sectors_srcunit_tex_op_red.avg.pct_of_peak_sustained_elapsed',
-        'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum', 'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum',
-        'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum',
-        'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
-        'smsp__warps_eligible.avg.per_cycle_active', 'smsp__warps_active.avg.per_cycle_active',
-        'l1tex__t_bytes_pipe_lsu_mem_local_op_ld.sum', 'l1tex__t_bytes_pipe_lsu_mem_local_op_st.sum']
-cols = {}
+#!/usr/bin/env python
+"""Markdown summary of ncu --set full reports (one kernel launch each): the metrics profiles/*.md quote.
+usage: ncu_summary.py label=path.ncu-rep ... > profiles/ncu_summary_rNN.md"""
+import csv
+import subprocess
+import sys
+
+M = [("duration", "gpu__time_duration.sum"), ("grid", "launch__grid_size"), ("block", "launch__block_size"),
+     ("regs/thread", "launch__registers_per_thread"), ("warps active % of peak", "sm__warps_active.avg.pct_of_peak_sustained_active"),
+     ("issue slots busy %", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+     ("FP64 pipe % (sm__inst_executed_pipe_fp64)", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+     ("tensor pipe cycles active %", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+     ("LSU pipe %", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+     ("L1 data-pipe wavefronts % (l1tex__data_pipe_lsu_wavefronts)", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+     ("active lanes per instruction", "smsp__thread_inst_executed_per_inst_executed.ratio"),
+     ("warp instructions", "smsp__inst_executed.sum"),
+     ("DFMA thread-instr", "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"),
+     ("DMUL thread-instr", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"),
+     ("DADD thread-instr", "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"),
+     ("local loads (warp instr)", "smsp__sass_inst_executed_op_local_ld.sum"), ("local stores (warp instr)", "smsp__sass_inst_executed_op_local_st.sum"),
+     ("L1 hit %", "l1tex__t_sector_hit_rate.pct"), ("L2 hit %", "lts__t_sector_hit_rate.pct"),
+     ("DRAM read", "dram__bytes_read.sum"), ("DRAM write", "dram__bytes_write.sum"),
+     ("DRAM throughput % of peak", "dram__throughput.avg.pct_of_peak_sustained_elapsed"),
+     ("SM active cycles avg", "sm__cycles_active.avg"), ("SM active cycles max", "sm__cycles_active.max")]
+
+
+def raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(out.splitlines()))
+    return r[0], r[1], r[2:]
+
+
+cols = []
 for arg in sys.argv[1:]:
-    tag, f = arg.split(':')
-    txt = subprocess.run(['ncu', '-i', f, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(txt)))
-    hdr, units, vals = rows[0], rows[1], rows[-1]
-    cols[tag] = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
-tags = list(cols)
-print('| metric | ' + ' | '.join(tags) + ' |')
-print('|---|' + '---|' * len(tags))
-for w in WANT:
-    if all(w in cols[t] for t in tags):
-        def fmt(v):
-            try:
-                x = float(v); return f'{x:.4g}'
-            except ValueError:
-                return v
-        print(f'| {w} [{cols[tags[0]][w][1]}] | ' + ' | '.join(fmt(cols[t][w][0]) for t in tags) + ' |')
+    label, path = arg.split("=", 1)
+    h, u, rows = raw(path)
+    for r in rows:
+        d = {k: (v, un) for k, v, un in zip(h, r, u)}
+        cols.append((label if len(rows) == 1 else f"{label} #{rows.index(r)}", d))
+print("| metric | " + " | ".join(c[0] for c in cols) + " |")
+print("|---|" + "---|" * len(cols))
+print("| kernel | " + " | ".join("`" + c[1]["Kernel Name"][0].split("(")[0][-60:] + "`" for c in cols) + " |")
+for name, key in M:
+    vals = []
+    for _, d in cols:
+        if key not in d:
+            vals.append("-")
+            continue
+        v, un = d[key]
+        try:
+            f = float(v)
+            v = f"{f:.4g}" if abs(f) < 1e6 else f"{f:.4e}"
+        except ValueError:
+            pass
+        vals.append(f"{v} {un}".strip())
+    print(f"| {name} | " + " | ".join(vals) + " |")
+# executed FP64 flops = 2 DFMA + DMUL + DADD
+vals = []
+for _, d in cols:
+    try:
+        fl = 2 * float(d["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"][0]) + float(d["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"][0]) + \
+             float(d["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"][0])
+        t = float(d["gpu__time_duration.sum"][0])
+        un = d["gpu__time_duration.sum"][1]
+        t *= {"ns": 1e-9, "us": 1e-6, "usecond": 1e-6, "ms": 1e-3, "msecond": 1e-3, "s": 1.0, "second": 1.0, "nsecond": 1e-9}.get(un, 1e-9)
+        vals.append(f"{fl:.4e} flop, {fl / t * 1e-12:.2f} TFLOP/s under ncu")
+    except (KeyError, ValueError):
+        vals.append("-")
+print("| executed FP64 flops (2 DFMA + DMUL + DADD) | " + " | ".join(vals) + " |")
+# stall reasons
+vals = []
+for _, d in cols:
+    st = {k.replace("smsp__pcsamp_warps_issue_stalled_", ""): int(float(v[0])) for k, v in d.items()
+          if k.startswith("smsp__pcsamp_warps_issue_stalled_") and "not_issued" not in k}
+    tot = sum(st.values()) or 1
+    vals.append(", ".join(f"{k} {100 * x / tot:.0f}%" for k, x in sorted(st.items(), key=lambda t: -t[1])[:5]))
+print("| warp stall samples (top 5) | " + " | ".join(vals) + " |")

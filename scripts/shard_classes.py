@@ -36,4 +36,4 @@ for it in range(5):
     d = st.as_dict()["ms_class"]
     if it >= 2:
         acc = d if acc is None else {k: min(acc[k], v) for k, v in d.items()}
-print(name, nranks, os.environ.get("QLB_YS_TARGET", "-"), " ".join(f"{k}={v:.3f}" for k, v in acc.items()), "sum=%.3f" % sum(acc.values()), flush=True)
+print(name, nranks, os.environ.get("QLB_TPW", os.environ.get("QLB_YS_TARGET", "-")), " ".join(f"{k}={v:.3f}" for k, v in acc.items()), "sum=%.3f" % sum(acc.values()), flush=True)
