@@ -275,6 +275,8 @@ extern "C" int qlb_init(int device) {
     QLB_CUDA(cudaEventCreateWithFlags(&e.ev_join[i], cudaEventDisableTiming));
   }
   QLB_CUDA(cudaEventCreateWithFlags(&e.ev_fork, cudaEventDisableTiming));
+  QLB_CUDA(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking));
+  QLB_CUDA(cudaEventCreateWithFlags(&e.ev_copy, cudaEventDisableTiming));
   std::vector<double> tab;
   make_boys_table(tab);
   QLB_CUDA(cudaMalloc((void **)&e.d_boys, tab.size() * sizeof(double)));
@@ -310,6 +312,10 @@ extern "C" int qlb_finalize(void) {
       if (e.ev_join[i]) cudaEventDestroy(e.ev_join[i]);
     }
     if (e.ev_fork) cudaEventDestroy(e.ev_fork);
+    if (e.copy_stream) cudaStreamDestroy(e.copy_stream);
+    if (e.ev_copy) cudaEventDestroy(e.ev_copy);
+    e.copy_stream = nullptr;
+    e.ev_copy = nullptr;
     e = Engine();
   }
   g_cur = keep;
@@ -1089,8 +1095,12 @@ extern "C" int qlb_fock(qlb_basis *b, const double *H, const double *P, double t
   Engine &e = g_engine;
   const size_t N2 = (size_t)b->nbf * b->nbf;
   QLB_CUDA(cudaSetDevice(e.device));
-  QLB_CUDA(cudaMemcpyAsync(b->d_H, H, N2 * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  // H is only needed when F is assembled: its upload runs beside the build on the copy stream (the previous call has
+  // been synchronised, so d_H is free)
+  QLB_CUDA(cudaMemcpyAsync(b->d_H, H, N2 * sizeof(double), cudaMemcpyHostToDevice, e.copy_stream));
+  QLB_CUDA(cudaEventRecord(e.ev_copy, e.copy_stream));
   if (int rc = jk_host_common(b, P, tau, stats)) return rc;
+  QLB_CUDA(cudaStreamWaitEvent(e.stream, e.ev_copy, 0));
   // F overwrites the P scratch (P is no longer needed)
   if (int rc = qlb_fock_device(b, b->d_H, b->d_JK, b->d_JK + N2, b->d_P, e.stream)) return rc;
   if (stats) stats->kernel_launches += 1;

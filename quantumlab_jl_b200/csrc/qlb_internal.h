@@ -33,6 +33,8 @@ struct Engine {
   int nside = 7;
   cudaStream_t side_stream[NSIDE] = {nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {nullptr};
+  cudaStream_t copy_stream = nullptr;  // host -> device copies that overlap a build (the core Hamiltonian of qlb_fock)
+  cudaEvent_t ev_copy = nullptr;
   double *d_boys = nullptr;
   bool profiling = false;
   // tuning knobs, read from the environment once in qlb_init

@@ -14,9 +14,9 @@ M = [("duration", "gpu__time_duration.sum"), ("grid", "launch__grid_size"), ("bl
      ("L1 data-pipe wavefronts % (l1tex__data_pipe_lsu_wavefronts)", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
      ("active lanes per instruction", "smsp__thread_inst_executed_per_inst_executed.ratio"),
      ("warp instructions", "smsp__inst_executed.sum"),
-     ("DFMA thread-instr", "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"),
-     ("DMUL thread-instr", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"),
-     ("DADD thread-instr", "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"),
+     ("DFMA thread-instr per cycle (GPU)", "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed"),
+     ("DMUL thread-instr per cycle (GPU)", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed"),
+     ("DADD thread-instr per cycle (GPU)", "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed"),
      ("local loads (warp instr)", "smsp__sass_inst_executed_op_local_ld.sum"), ("local stores (warp instr)", "smsp__sass_inst_executed_op_local_st.sum"),
      ("L1 hit %", "l1tex__t_sector_hit_rate.pct"), ("L2 hit %", "lts__t_sector_hit_rate.pct"),
      ("DRAM read", "dram__bytes_read.sum"), ("DRAM write", "dram__bytes_write.sum"),
@@ -54,16 +54,18 @@ for name, key in M:
             pass
         vals.append(f"{v} {un}".strip())
     print(f"| {name} | " + " | ".join(vals) + " |")
-# executed FP64 flops = 2 DFMA + DMUL + DADD
+# executed FP64 flops = 2 DFMA + DMUL + DADD (thread instructions per cycle x elapsed cycles)
 vals = []
 for _, d in cols:
     try:
-        fl = 2 * float(d["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"][0]) + float(d["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"][0]) + \
-             float(d["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"][0])
+        pc = 2 * float(d["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed"][0]) + \
+             float(d["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed"][0]) + \
+             float(d["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed"][0])
+        cyc = float(d["sm__cycles_elapsed.max"][0])
         t = float(d["gpu__time_duration.sum"][0])
         un = d["gpu__time_duration.sum"][1]
         t *= {"ns": 1e-9, "us": 1e-6, "usecond": 1e-6, "ms": 1e-3, "msecond": 1e-3, "s": 1.0, "second": 1.0, "nsecond": 1e-9}.get(un, 1e-9)
-        vals.append(f"{fl:.4e} flop, {fl / t * 1e-12:.2f} TFLOP/s under ncu")
+        vals.append(f"{pc * cyc:.4e} flop = {pc * cyc / t * 1e-12:.2f} TFLOP/s under ncu ({100 * pc / (148 * 128):.1f} % of 148 x 64 DFMA/clk)")
     except (KeyError, ValueError):
         vals.append("-")
 print("| executed FP64 flops (2 DFMA + DMUL + DADD) | " + " | ".join(vals) + " |")
