@@ -16,6 +16,16 @@ from . import libqlb
 from .shell import Shell, flattenShells, totalBasisFunctions
 
 DEFAULT_TAU = 1e-12  # Schwarz x density threshold (protects the 1e-10 per-element parity)
+MAX_L = 2            # QLB_MAX_L of include/qlb200.h: orbital shells up to d (the RI auxiliary index goes to f)
+
+
+def _check_orbital_L(shells):
+    """The class kernels exist for s, p and d orbital shells; name the offender instead of a bare C error code."""
+    for i, s in enumerate(shells):
+        if s.lqn.exponent > MAX_L:
+            raise ValueError(f"shell {i} (L = {s.lqn.exponent}, center {tuple(s.center)}) exceeds the orbital angular momentum "
+                             f"this library is built for (QLB_MAX_L = {MAX_L}: s, p, d); f and higher shells are only supported "
+                             f"on the RI auxiliary index")
 
 
 class B200Shells(list):
@@ -23,6 +33,7 @@ class B200Shells(list):
         super().__init__(shells)
         if not all(isinstance(s, Shell) for s in self):
             raise TypeError("B200Shells takes a sequence of Shell")
+        _check_orbital_L(self)
         lib = libqlb.init(device)
         self._arrays = flattenShells(list(self))  # keep alive
         centers, L, nprim, exps, coefs = self._arrays
@@ -154,6 +165,7 @@ class B200MultiShells(list):
 
     def __init__(self, shells, ngpu: int, tau: float = DEFAULT_TAU):
         super().__init__(shells)
+        _check_orbital_L(self)
         lib = libqlb.load()
         self._arrays = flattenShells(list(self))
         centers, L, nprim, exps, coefs = self._arrays

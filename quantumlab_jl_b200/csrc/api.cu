@@ -528,17 +528,18 @@ static int basis_build_pairs(qlb_basis *b) {
   QLB_CUDA(cudaMemcpy(b->d_pair_qls, b->h_pair_qls.data(), b->npairs * sizeof(int), cudaMemcpyHostToDevice));
   {
     // packed per-pair records (eri_kernels.cuh: load_pair_info)
-    std::vector<double2> info((size_t)5 * std::max<int64_t>(b->npairs, 1));
+    std::vector<double2> info((size_t)PAIR_INFO_BLOCK * std::max<int64_t>((b->npairs + 31) / 32, 1));
     for (int64_t i = 0; i < b->npairs; ++i) {
       const int pa_ = b->h_pair_a[i], pb_ = b->h_pair_b[i];
       const double *A = &b->h_xyz[3 * pa_], *B = &b->h_xyz[3 * pb_];
-      info[5 * i + 0] = make_double2(A[0], A[1]);
-      info[5 * i + 1] = make_double2(A[2], B[0]);
-      info[5 * i + 2] = make_double2(B[1], B[2]);
+      double2 *r = &info[(size_t)(i >> 5) * PAIR_INFO_BLOCK + (i & 31)];
+      r[0] = make_double2(A[0], A[1]);
+      r[32] = make_double2(A[2], B[0]);
+      r[64] = make_double2(B[1], B[2]);
       const int i3[4] = {pa_, pb_, b->h_pair_poff[i], b->h_pair_np[i]};
       const int i4[4] = {b->h_boff[pa_], b->h_boff[pb_], b->h_pair_ql[i], 0};
-      memcpy(&info[5 * i + 3], i3, 16);
-      memcpy(&info[5 * i + 4], i4, 16);
+      memcpy(&r[96], i3, 16);
+      memcpy(&r[128], i4, 16);
     }
     if (b->d_pair_info) cudaFree(b->d_pair_info);
     b->d_pair_info = nullptr;

@@ -62,7 +62,7 @@ struct ClassParams {
   const int *__restrict__ pair_ql;     // qlog(Q_ab)
   const int *__restrict__ pair_qls;    // max of pair_ql over this and every LATER pair of the class (non-increasing: ends walks)
   const int *__restrict__ pair_dl;     // per build: qlog(max |P|) over the pair's own shell block (coalesced in the walk)
-  // packed per-pair record, 5 x 16 B: {Ax,Ay} {Az,Bx} {By,Bz} int4{a,b,poff,np} int4{fa,fb,ql,0}: what a batch needs about a
+  // packed per-pair record, 5 x 16 B (field-major in blocks of 32 pairs, see load_pair_info): {Ax,Ay} {Az,Bx} {By,Bz} int4{a,b,poff,np} int4{fa,fb,ql,0}: what a batch needs about a
   // ket pair arrives with 5 vector loads instead of 14 scattered scalar ones (ncu: the light classes are bound by L1
   // wavefronts of exactly those gathers)
   const double2 *__restrict__ pair_info;
@@ -95,10 +95,15 @@ struct PairInfo {  // unpacked pair_info record
   double Ax, Ay, Az, Bx, By, Bz;
   int a, b, poff, np, fa, fb, ql;
 };
+// Layout: blocks of 32 consecutive pairs, field-major inside a block ([block][field 0..4][pair]), so that the survivors of
+// a batch -- which come from two or three ket tiles -- share cache lines per field load (80-byte records per pair made
+// every lane of the five loads touch its own line: ncu, 160 L1 wavefronts per batch, as many as the primitive loop of a
+// K = 10 batch).
+constexpr int PAIR_INFO_BLOCK = 5 * 32;  // double2 per block of 32 pairs
 __device__ __forceinline__ PairInfo load_pair_info(const double2 *__restrict__ info, int g) {
-  const double2 *r = info + (size_t)5 * g;
-  const double2 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
-  const int4 i3 = __ldg(reinterpret_cast<const int4 *>(r + 3)), i4 = __ldg(reinterpret_cast<const int4 *>(r + 4));
+  const double2 *r = info + (size_t)(g >> 5) * PAIR_INFO_BLOCK + (g & 31);
+  const double2 r0 = __ldg(r), r1 = __ldg(r + 32), r2 = __ldg(r + 64);
+  const int4 i3 = __ldg(reinterpret_cast<const int4 *>(r + 96)), i4 = __ldg(reinterpret_cast<const int4 *>(r + 128));
   PairInfo o;
   o.Ax = r0.x; o.Ay = r0.y; o.Az = r1.x; o.Bx = r1.y; o.By = r2.x; o.Bz = r2.y;
   o.a = i3.x; o.b = i3.y; o.poff = i3.z; o.np = i3.w; o.fa = i4.x; o.fb = i4.y; o.ql = i4.z;

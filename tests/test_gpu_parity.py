@@ -235,8 +235,15 @@ def test_bad_arguments_raise(qlb):
     from quantumlab_jl_b200.base import LQuantumNumber, origin
     from quantumlab_jl_b200.shell import Shell
 
-    with pytest.raises(qlb.QlbError):
+    with pytest.raises(ValueError, match="QLB_MAX_L"):  # the host mirror names the offending shell ...
         _b200([Shell(origin, LQuantumNumber("F"), [1.0], [1.0])])  # L > QLB_MAX_L, cf. LibInt2Module.jl:79-83
+    import ctypes as C
+
+    lib = qlb.init(-1)
+    c, L_, n, e, k = (np.zeros(3), np.array([3], dtype=np.int32), np.array([1], dtype=np.int32), np.ones(1), np.ones(1))
+    h = C.c_void_p()
+    with pytest.raises(qlb.QlbError):                   # ... and the C ABI rejects it on its own
+        qlb.check(lib.qlb_basis_create(1, qlb.dptr(c), qlb.iptr(L_), qlb.iptr(n), qlb.dptr(e), qlb.dptr(k), C.byref(h)))
     dev = _b200([Shell(origin, LQuantumNumber("S"), [1.0], [1.0])])
     with pytest.raises(ValueError):
         dev.build_jk(np.zeros((3, 3)))

@@ -116,3 +116,17 @@ def test_function_lists_regroup_into_device_shells():
     fm3 = FunctionMap(pick)
     assert len(fm3.shells) == 4
     assert identityCGF.primitiveBFs[0].exponent == 0.0 and identityCGF.coefficients == [1.0]
+
+
+def test_orbital_f_shell_is_rejected_by_name():
+    """QLB_MAX_L = 2 on the orbital index: the host mirror names the offending shell before any device call."""
+    import pytest
+
+    from quantumlab_jl_b200.b200shells import B200Shells
+    from quantumlab_jl_b200.base import LQuantumNumber, Position
+    from quantumlab_jl_b200.shell import Shell
+
+    s = Shell(Position(0.0, 0.0, 0.0), LQuantumNumber("S"), [1.0], [1.0])
+    f = Shell(Position(0.0, 0.0, 1.0), LQuantumNumber("F"), [0.8], [1.0])
+    with pytest.raises(ValueError, match="shell 1 .L = 3"):
+        B200Shells([s, f])
