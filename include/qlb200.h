@@ -99,7 +99,8 @@ int qlb_schwarz(qlb_basis *b, double *Q);
  *   fused pass over the unique, screened quartets.  Host buffers N x N; J or K may be NULL.
  *   A quartet (ab|cd) is evaluated iff qlog(Q_ab) + qlog(Q_cd) + max qlog(|P| over the six shell blocks
  *   ab,cd,ac,ad,bc,bd) >= qlog(tau), qlog(x) = ceil(8*log2 x): integer arithmetic, so counts are reproducible.
- *   tau <= 0 switches screening off.
+ *   tau <= 0 switches screening off.  P MUST be symmetric: the kernels digest one triangle of P and symmetrise J and K
+ *   afterwards (the reference's nsh^4 loop would also accept a non-symmetric matrix; the host mirror rejects one).
  * qlb_fock replaces computeMatrixFock (SpecialMatricesModule.jl:284-290): F = H + 2J - K with H = T + V. */
 int qlb_build_jk(qlb_basis *b, const double *P, double tau, double *J, double *K, qlb_stats *stats);
 int qlb_fock(qlb_basis *b, const double *H, const double *P, double tau, double *F, qlb_stats *stats);

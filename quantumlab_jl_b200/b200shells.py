@@ -74,6 +74,11 @@ class B200Shells(list):
         P = np.asfortranarray(P, dtype=np.float64)
         if P.shape != (self.nbf, self.nbf):
             raise ValueError(f"density matrix must be {self.nbf}x{self.nbf}, got {P.shape}")
+        # the kernels read one triangle of P and symmetrise J and K afterwards (every SCF density is symmetric); the
+        # reference's nsh^4 loop also accepts a non-symmetric matrix -- refuse it instead of answering for its symmetric part
+        scale = float(np.abs(P).max()) if P.size else 0.0
+        if scale > 0.0 and float(np.abs(P - P.T).max()) > 1e-10 * scale:
+            raise ValueError("density matrix must be symmetric (the device path digests one triangle of P)")
         return P
 
     def build_jk(self, P, tau: float | None = None, want_stats: bool = True):

@@ -247,6 +247,10 @@ def test_bad_arguments_raise(qlb):
     dev = _b200([Shell(origin, LQuantumNumber("S"), [1.0], [1.0])])
     with pytest.raises(ValueError):
         dev.build_jk(np.zeros((3, 3)))
+    two = _b200([Shell(origin, LQuantumNumber("S"), [1.0], [1.0]), Shell(origin, LQuantumNumber("S"), [0.3], [1.0])])
+    with pytest.raises(ValueError, match="symmetric"):
+        two.build_jk(np.array([[1.0, 0.2], [0.1, 1.0]]))
+    two.destroy()
     with pytest.raises(qlb.QlbError):
         dev.eri_block(0, 0, 0, 5)
     dev.destroy()
