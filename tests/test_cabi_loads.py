@@ -77,6 +77,16 @@ def test_multirank_schedule_covers_every_piece_once():
                 assert (owner[qc, :npieces[qc]] < nranks).all()
             if nranks > 1:
                 assert len(set(owner[owner >= 0].tolist())) == nranks  # every rank got work
+            # a class whose per-rank share reaches 0.12 ms is dealt by rows: one piece per rank, every rank once
+            for qc in range(21):
+                if gc[qc] >= 0.12 * nranks:
+                    assert npieces[qc] == nranks and sorted(owner[qc].tolist()) == list(range(nranks))
+            # ... so the modelled load is balanced to within the small classes
+            load = np.zeros(nranks)
+            for qc in range(21):
+                for p_ in range(npieces[qc]):
+                    load[owner[qc, p_]] += gc[qc] / npieces[qc]
+            assert load.max() - load.min() <= 0.12 * nranks + 1e-12
 
 
 def test_qlog_bit_exact_between_library_and_oracle(orc):
