@@ -240,18 +240,27 @@ __device__ __forceinline__ void bra_contract(const double *__restrict__ Es, cons
     constexpr int iab = decltype(abc)::value, ia = iab % NA, ib = iab / NA;
     constexpr int ax = cart_x(LA, ia), ay = cart_y(LA, ia), az = LA - ax - ay;
     constexpr int bbx = cart_x(LB, ib), bby = cart_y(LB, ib), bbz = LB - bbx - bby;
-    double s = 0.0;
+    // straight into the accumulator (no s = 0; ...; acc += s), and the E_000 = 1 factors of an axis without angular
+    // momentum are skipped at compile time: the staged coefficients are run-time values, so nvcc cannot fold them
+    constexpr bool one_x = (ax + bbx == 0), one_y = (ay + bby == 0), one_z = (az + bbz == 0);
+    double s = acc[iab];
 #pragma unroll
     for (int t = 0; t <= ax + bbx; ++t)
 #pragma unroll
       for (int u = 0; u <= ay + bby; ++u) {
-        const double exy = Ex[(ax * (LB + 1) + bbx) * (LAB + 1) + t] * Ey[(ay * (LB + 1) + bby) * (LAB + 1) + u];
-        double sv = 0.0;
+        double sv;
+        if constexpr (one_z) sv = G[hidx(LAB, t, u, 0)];
+        else {
+          sv = Ez[(az * (LB + 1) + bbz) * (LAB + 1)] * G[hidx(LAB, t, u, 0)];
 #pragma unroll
-        for (int v = 0; v <= az + bbz; ++v) sv = fma(Ez[(az * (LB + 1) + bbz) * (LAB + 1) + v], G[hidx(LAB, t, u, v)], sv);
-        s = fma(exy, sv, s);
+          for (int v = 1; v <= az + bbz; ++v) sv = fma(Ez[(az * (LB + 1) + bbz) * (LAB + 1) + v], G[hidx(LAB, t, u, v)], sv);
+        }
+        if constexpr (one_x && one_y) s += sv;
+        else if constexpr (one_x) s = fma(Ey[(ay * (LB + 1) + bby) * (LAB + 1) + u], sv, s);
+        else if constexpr (one_y) s = fma(Ex[(ax * (LB + 1) + bbx) * (LAB + 1) + t], sv, s);
+        else s = fma(Ex[(ax * (LB + 1) + bbx) * (LAB + 1) + t] * Ey[(ay * (LB + 1) + bby) * (LAB + 1) + u], sv, s);
       }
-    acc[iab] += s;
+    acc[iab] = s;
   });
 }
 
