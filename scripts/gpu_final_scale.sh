@@ -10,4 +10,4 @@ import json; d=json.load(open('${T}_$1.json')); print('$1', d['n_gpus'], round(d
 }
 run h2o32_631gs 10 "--cpu-seconds 0"
 run c40h82_def2svp 10 "--cpu-seconds 0"
-if [ "$N" = "8" ]; then run h2o64_ccpvdz 5 "--cpu-seconds 0"; run h2o64_ccpvdz_rijk 3 ""; fi
+if [ "$N" = "8" ] && [ -n "$FULL" ]; then run h2o64_ccpvdz 5 "--cpu-seconds 0"; run h2o64_ccpvdz_rijk 3 ""; fi
