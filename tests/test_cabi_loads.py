@@ -110,3 +110,30 @@ def test_qlog_bit_exact_between_library_and_oracle(orc):
     # and it is ceil(8 log2 x) away from the last-ulp neighbourhood of a bin edge
     for x in (1e-12, 3.7, 123.456, 1e-5, 0.3, 7.0):
         assert lib.qlb_qlog(x) == math.ceil(8 * math.log2(x))
+
+
+def test_julia_binding_calls_only_declared_symbols():
+    """julia/QuantumLabB200.jl cannot be executed in this image (no Julia): at least every symbol it ccalls must be
+    declared in include/qlb200.h and exported by the library, and every reference function it extends must exist in the
+    reference's module it imports from."""
+    import os
+    import re
+
+    from quantumlab_jl_b200 import libqlb
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    jl = open(os.path.join(root, "julia", "QuantumLabB200.jl")).read()
+    hdr = open(os.path.join(root, "include", "qlb200.h")).read()
+    called = set(re.findall(r":(qlb_[a-z0-9_]+)", jl))
+    declared = set(re.findall(r"\b(qlb_[a-z0-9_]+)\s*\(", hdr))
+    assert called and not (called - declared), sorted(called - declared)
+    lib = libqlb.load()
+    assert all(hasattr(lib, n) for n in called)
+    # in the build container the reference checkout is present: every `import ..XModule: f, g` names a function that
+    # module defines (the GPU box has no /root/reference; this part is skipped there)
+    ref = "/root/reference/src/SubModules"
+    if os.path.isdir(ref):
+        for mod, names in re.findall(r"^import \.\.(\w+):((?:[^\n#]*(?:#[^\n]*)?\n(?=\s{10,}))*[^\n#]*)", jl, flags=re.M):
+            src = open(os.path.join(ref, mod + ".jl")).read()
+            for name in re.findall(r"[A-Za-z_][A-Za-z0-9_!]*", re.sub(r"#[^\n]*", "", names)):
+                assert re.search(r"(function\s+|^\s*)" + re.escape(name) + r"\s*\(", src, flags=re.M), (mod, name)
